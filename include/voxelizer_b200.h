@@ -1,0 +1,163 @@
+/* voxelizer_b200 -- C ABI of the B200 backend for jbehley/voxelizer's gen_data hot path.
+ *
+ * The reference (single-threaded C++, no FFI of its own) runs this path behind plain classes:
+ *   gen_data frame loop                 src/gen_data.cpp:62-142
+ *   fillVoxelGrid                       src/data/voxelize_utils.cpp:173-203
+ *   VoxelGrid::insert / clear           src/data/VoxelGrid.cpp:30-63
+ *   VoxelGrid::updateOcclusions         src/data/VoxelGrid.cpp:98-171
+ *   VoxelGrid::updateInvalid            src/data/VoxelGrid.cpp:173-233
+ *   VoxelGrid::occludedBy               src/data/VoxelGrid.cpp:235-316
+ *   saveVoxelGrid / pack                src/data/voxelize_utils.cpp:205-296
+ * This library replaces exactly that path.  It sits BELOW the reference's Eigen pose algebra: the
+ * caller computes, per scan of a frame's window, ap = anchor_pose.inverse() * pose
+ * (voxelize_utils.cpp:183) and the endpoint (gen_data.cpp:114) on the host and passes the numbers in,
+ * so the GPU never has to reproduce Eigen's 4x4 inverse.  The C++ facade in voxelizer_b200/host keeps
+ * the reference's own API (VoxelGrid, fillVoxelGrid, saveVoxelGrid, Config, KittiReader) on top of it.
+ *
+ * Conventions: every entry point returns 0 on success or a negative vx_status; CUDA failures are
+ * reported, never papered over -- there is NO CPU fallback.  Matrices are 16 floats, column-major
+ * (Eigen::Matrix4f storage order).  The caller owns all host buffers; the library owns all device
+ * memory.  One context per GPU; calls on one context must be serialised by the caller.
+ * All outputs are byte-identical to the files the reference writes.
+ */
+#ifndef VOXELIZER_B200_H_
+#define VOXELIZER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vx_ctx vx_ctx;
+
+typedef enum vx_status {
+  VX_OK = 0,
+  VX_ERR_INVALID = -1,        /* bad argument */
+  VX_ERR_CUDA = -2,           /* a CUDA runtime call or kernel failed; see vx_last_error */
+  VX_ERR_NO_DEVICE = -3,      /* no usable CUDA device: the library does not run on the CPU */
+  VX_ERR_UNKNOWN_SCAN = -4,   /* a frame references a scan id that is not resident */
+  VX_ERR_TABLE_OVERFLOW = -5, /* histogram table could not be grown any further */
+  VX_ERR_UNSUPPORTED = -6     /* grid too large for the traversal's visit counter (> 2^25 visits) */
+} vx_status;
+
+/* Grid geometry = the arguments of VoxelGrid::initialize(resolution, min, max)
+ * (VoxelGrid.cpp:5-28); sizes and offset are derived inside with the reference's arithmetic. */
+typedef struct vx_grid_desc {
+  float resolution;    /* Config::voxelSize  */
+  float min_extent[3]; /* Config::minExtent  */
+  float max_extent[3]; /* Config::maxExtent  */
+} vx_grid_desc;
+
+/* Point filters of fillVoxelGrid (voxelize_utils.cpp:175-201). */
+typedef struct vx_filter_desc {
+  float min_range;                 /* Config::minRange */
+  float max_range;                 /* Config::maxRange */
+  int32_t hidecar;                 /* Config::hidecar (ego-vehicle box -2 < x < 3, |y| < 2) */
+  const uint32_t* filtered_labels; /* Config::filteredLabels ("ignore") */
+  uint32_t n_filtered;
+  const uint32_t* join_pairs; /* Config::joinedLabels flattened as (key, member) pairs in map order */
+  uint32_t n_join_pairs;
+} vx_filter_desc;
+
+/* Tuning knobs; zero-initialise for defaults. */
+typedef struct vx_options {
+  uint32_t frames_in_flight;     /* frame slots resident on the device (default 64) */
+  uint32_t table_log2_capacity;  /* initial (voxel,label) histogram slots per frame, log2 (default 21) */
+  uint32_t reserved[6];
+} vx_options;
+
+/* One target frame = one iteration of gen_data.cpp:62-142 that passed the "labelled" gate.
+ * prior_* describe priorPoints (the last one is the target scan), past_* describe pastPoints.
+ * Prior scans are inserted into BOTH grids, past scans into the target grid only
+ * (gen_data.cpp:96-98).  endpoints[i] = (anchor^-1 * pose_past[i]).col(3).head(3), one
+ * VoxelGrid::updateInvalid pass each, in this order (gen_data.cpp:113-116).
+ * Output pointers may be NULL to skip that product; sizes are vx_output_bytes(). */
+typedef struct vx_frame_desc {
+  uint32_t n_prior;
+  const uint32_t* prior_ids;
+  const float* ap_prior; /* n_prior x 16 */
+  uint32_t n_past;
+  const uint32_t* past_ids;
+  const float* ap_past;   /* n_past x 16 */
+  uint32_t n_endpoints;   /* updateInvalid calls; gen_data: one per past scan (= n_past) */
+  const float* endpoints; /* n_endpoints x 3 */
+  uint8_t* out_bin;       /* <name>.bin       nvox/8 bytes  (input grid, majority label > 0) */
+  uint16_t* out_label;    /* <name>.label     nvox uint16   (target grid majority label)     */
+  uint8_t* out_occluded;  /* <name>.occluded  nvox/8 bytes                                   */
+  uint8_t* out_invalid;   /* <name>.invalid   nvox/8 bytes                                   */
+} vx_frame_desc;
+
+typedef struct vx_grid_info {
+  uint32_t size[3]; /* Sx, Sy, Sz */
+  float offset[3];
+  float resolution;
+  uint64_t num_voxels;
+  uint64_t packed_bytes; /* num_voxels / 8 */
+  uint64_t label_bytes;  /* num_voxels * 2 */
+} vx_grid_info;
+
+/* Accumulated device time per stage (CUDA events on the library's stream) since the last reset. */
+typedef struct vx_stage_times {
+  double fill_ms;       /* K1+K2: transform, filter, key, histogram insert */
+  double vote_ms;       /* K3: per-voxel majority vote                      */
+  double emit_ms;       /* K5: label / .bin / occupancy emit + table reset  */
+  double visibility_ms; /* K4: occlusion + invalid passes                   */
+  double pack_ms;       /* K5: .occluded / .invalid bit-pack                */
+  double total_ms;      /* whole batches, first kernel to last copy         */
+  uint64_t frames;
+  uint64_t points_read;   /* window points streamed by the fill kernel */
+  uint64_t fill_launches; /* kernel launches per stage */
+  uint64_t vote_launches;
+  uint64_t emit_launches;
+  uint64_t visibility_launches;
+  uint64_t pack_launches;
+  uint64_t rays_cast; /* occludedBy calls (all passes) */
+  uint64_t dda_steps; /* cells traversed by those rays */
+} vx_stage_times;
+
+const char* vx_last_global_error(void); /* for failures before a context exists */
+const char* vx_last_error(const vx_ctx* ctx);
+
+int vx_device_count(void);
+int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter, const vx_options* options, vx_ctx** out);
+void vx_destroy(vx_ctx* ctx);
+int vx_grid_info_get(const vx_ctx* ctx, vx_grid_info* out);
+uint32_t vx_frames_in_flight(const vx_ctx* ctx); /* frames one internal batch holds */
+
+/* Pinned host memory helpers for the output ring / scan staging. */
+void* vx_host_alloc(size_t bytes);
+void vx_host_free(void* p);
+
+/* Device-resident scan cache (replaces KittiReader's pointsCache_/labelCache_, KittiReader.cpp:73-142).
+ * xyzr: n x 4 float32 exactly as in a KITTI velodyne .bin (KittiReader.cpp:145-171); labels: n raw
+ * uint32 words of the .label file -- the library applies the reader's "& 0xFFFF" (KittiReader.cpp:189). */
+int vx_upload_scan(vx_ctx* ctx, uint32_t scan_id, const float* xyzr, const uint32_t* labels, uint32_t n);
+int vx_evict_scan(vx_ctx* ctx, uint32_t scan_id);
+int vx_evict_all(vx_ctx* ctx);
+
+/* Runs n frames (any n; processed in batches of frames_in_flight).  Asynchronous with respect to the
+ * host only until the outputs of the last batch are being copied; returns after all outputs landed. */
+int vx_process_frames(vx_ctx* ctx, const vx_frame_desc* frames, uint32_t n);
+int vx_sync(vx_ctx* ctx);
+
+int vx_stage_times_get(vx_ctx* ctx, vx_stage_times* out);
+int vx_stage_times_reset(vx_ctx* ctx);
+
+/* Parity hooks: internals of frame `frame_index` of the LAST vx_process_frames call (must have been
+ * the last batch, i.e. n <= frames_in_flight).  Index order is the output order
+ * L = (x*Sy + y)*Sz + z.  dst may be NULL to query the required element count (returned via *count). */
+typedef enum vx_dump_kind {
+  VX_DUMP_HIST_TARGET = 0, /* uint32 triples (L, label, count), unordered         */
+  VX_DUMP_HIST_INPUT = 1,
+  VX_DUMP_OCCUPANCY = 2,   /* uint8 per voxel, target grid count > 0               */
+  VX_DUMP_OCCLUDED = 3,    /* uint8 per voxel, isOccluded                          */
+  VX_DUMP_INVALID = 4      /* uint8 per voxel, isInvalid                           */
+} vx_dump_kind;
+int vx_debug_dump(vx_ctx* ctx, uint32_t frame_index, int kind, void* dst, uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXELIZER_B200_H_ */

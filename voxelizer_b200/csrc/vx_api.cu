@@ -1,0 +1,619 @@
+// C ABI of the B200 backend (include/voxelizer_b200.h): context, device-resident scan cache, frame
+// slots and the batch pipeline  fill -> vote -> emit -> visibility -> pack -> copy-out.
+// Host-side only; the kernels live in vx_fill.cu / vx_visibility.cu.  No CPU fallback anywhere: if
+// CUDA is unusable every entry point reports VX_ERR_NO_DEVICE / VX_ERR_CUDA.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/voxelizer_b200.h"
+#include "vx_launch.h"
+
+namespace {
+
+std::string g_global_error;
+
+struct DeviceScan {
+  float4* points = nullptr;
+  uint32_t* labels = nullptr;
+  uint32_t n = 0;
+};
+
+struct SlotMem {
+  void* arena = nullptr;
+  size_t bytes = 0;
+  VxSlot dev{};  // device pointers
+};
+
+enum { EV_BEGIN = 0, EV_FILL, EV_VOTE, EV_EMIT, EV_VIS, EV_PACK, EV_END, EV_COUNT };
+
+// per-slot counter block (uint32 words): used/overflow of both tables, then two 64-bit statistics
+constexpr size_t kCounterWords = 8;
+
+}  // namespace
+
+struct vx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  VxGridGeom geom{};
+  uint64_t nvox = 0;
+  uint32_t words = 0;
+  float min_extent[3]{}, max_extent[3]{};
+
+  VxFilterDev filter{};
+  uint32_t* d_reject_bits = nullptr;
+
+  std::unordered_map<uint32_t, DeviceScan> scans;
+
+  uint32_t max_slots = 0;
+  uint32_t log2_target = 21, log2_input = 18;
+  bool keep_tables = false;
+  bool tables_dirty = false;  // tables hold the previous batch (debug mode)
+  uint32_t dirty_slots = 0;
+  std::vector<SlotMem> slots;
+  VxSlot* d_slots = nullptr;
+  uint32_t d_slots_cap = 0;
+  uint32_t* d_counters = nullptr;  // max_slots * kCounterWords
+  uint32_t* h_counters = nullptr;  // pinned mirror
+
+  // batch staging (items, ap, endpoints, vis frames): pinned host + device mirror
+  unsigned char* h_stage = nullptr;
+  unsigned char* d_stage = nullptr;
+  size_t stage_cap = 0;
+
+  cudaEvent_t ev[EV_COUNT]{};
+  vx_stage_times times{};
+  uint32_t last_batch = 0;
+  std::string error;
+};
+
+namespace {
+
+int fail(vx_ctx* c, int code, const std::string& msg) {
+  if (c) c->error = msg;
+  else g_global_error = msg;
+  return code;
+}
+
+#define VX_CUDA(ctx, call)                                                                         \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail((ctx), VX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// VoxelGrid::initialize (VoxelGrid.cpp:8-18): sizes by float ceil, offset with the double-precision
+// "0.5 *" of the reference.  Host code (x86-64, no FMA contraction of separate statements).
+void derive_geometry(const vx_grid_desc& d, VxGridGeom& g) {
+  g.res = d.resolution;
+  volatile float sx = std::ceil((d.max_extent[0] - d.min_extent[0]) / d.resolution);
+  volatile float sy = std::ceil((d.max_extent[1] - d.min_extent[1]) / d.resolution);
+  volatile float sz = std::ceil((d.max_extent[2] - d.min_extent[2]) / d.resolution);
+  const uint32_t n[3] = {(uint32_t)sx, (uint32_t)sy, (uint32_t)sz};
+  g.nx = (int32_t)n[0];
+  g.ny = (int32_t)n[1];
+  g.nz = (int32_t)n[2];
+  for (int a = 0; a < 3; ++a) {
+    volatile float span = d.max_extent[a] - d.min_extent[a];
+    volatile float cover = (float)n[a] * d.resolution;
+    volatile float slack = cover - span;
+    g.off[a] = (float)((double)d.min_extent[a] - 0.5 * (double)slack);
+  }
+}
+
+size_t table_bytes(uint32_t log2_cap) {
+  const size_t cap = (size_t)1 << log2_cap;
+  return align_up(cap * 8, 256) + align_up(cap * 4, 256) + align_up(cap * 4, 256);
+}
+
+size_t slot_bytes(const vx_ctx* c) {
+  const size_t nv = c->nvox, w = c->words;
+  return table_bytes(c->log2_target) + table_bytes(c->log2_input) + 2 * align_up(nv * 8, 256) + 3 * align_up((size_t)w * 4, 256) +
+         align_up(nv * 4, 256) + align_up(nv * 2, 256) + 3 * align_up((size_t)w * 4, 256);
+}
+
+int alloc_slot(vx_ctx* c, uint32_t index) {
+  SlotMem& s = c->slots[index];
+  s.bytes = slot_bytes(c);
+  VX_CUDA(c, cudaMalloc(&s.arena, s.bytes));
+  unsigned char* p = static_cast<unsigned char*>(s.arena);
+  auto take = [&](size_t bytes) {
+    unsigned char* r = p;
+    p += align_up(bytes, 256);
+    return r;
+  };
+  auto carve_table = [&](VxTable& t, uint32_t log2_cap, uint32_t* counters) {
+    const size_t cap = (size_t)1 << log2_cap;
+    t.keys = reinterpret_cast<unsigned long long*>(take(cap * 8));
+    t.counts = reinterpret_cast<uint32_t*>(take(cap * 4));
+    t.used = reinterpret_cast<uint32_t*>(take(cap * 4));
+    t.used_count = counters;
+    t.overflow = counters + 1;
+    t.log2_cap = log2_cap;
+  };
+  uint32_t* cnt = c->d_counters + (size_t)index * kCounterWords;
+  carve_table(s.dev.target, c->log2_target, cnt + 0);
+  carve_table(s.dev.input, c->log2_input, cnt + 2);
+  s.dev.counters = reinterpret_cast<unsigned long long*>(cnt + 4);
+  s.dev.best_input = reinterpret_cast<unsigned long long*>(take(c->nvox * 8));
+  s.dev.best_target = reinterpret_cast<unsigned long long*>(take(c->nvox * 8));
+  s.dev.occ = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
+  s.dev.occl = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
+  s.dev.alive = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
+  s.dev.memo = reinterpret_cast<uint32_t*>(take(c->nvox * 4));
+  s.dev.out_label = reinterpret_cast<uint16_t*>(take(c->nvox * 2));
+  s.dev.out_bin = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
+  s.dev.out_occluded = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
+  s.dev.out_invalid = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
+  // empty tables, empty vote arrays
+  const size_t cap_t = (size_t)1 << c->log2_target, cap_i = (size_t)1 << c->log2_input;
+  VX_CUDA(c, cudaMemsetAsync(s.dev.target.keys, 0xFF, cap_t * 8, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(s.dev.target.counts, 0, cap_t * 4, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(s.dev.input.keys, 0xFF, cap_i * 8, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(s.dev.input.counts, 0, cap_i * 4, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(s.dev.best_input, 0, c->nvox * 8, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(s.dev.best_target, 0, c->nvox * 8, c->stream));
+  return VX_OK;
+}
+
+void free_slots(vx_ctx* c) {
+  for (SlotMem& s : c->slots)
+    if (s.arena) cudaFree(s.arena);
+  c->slots.clear();
+  c->tables_dirty = false;
+}
+
+int ensure_slots(vx_ctx* c, uint32_t n) {
+  if (c->slots.size() >= n) return VX_OK;
+  const size_t old = c->slots.size();
+  c->slots.resize(n);
+  for (size_t i = old; i < n; ++i) {
+    const int rc = alloc_slot(c, (uint32_t)i);
+    if (rc != VX_OK) {
+      c->slots.resize(i);
+      return rc;
+    }
+  }
+  std::vector<VxSlot> host(n);
+  for (size_t i = 0; i < n; ++i) host[i] = c->slots[i].dev;
+  VX_CUDA(c, cudaMemcpyAsync(c->d_slots, host.data(), n * sizeof(VxSlot), cudaMemcpyHostToDevice, c->stream));
+  VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VX_OK;
+}
+
+int ensure_stage(vx_ctx* c, size_t bytes) {
+  if (bytes <= c->stage_cap) return VX_OK;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->d_stage) cudaFree(c->d_stage);
+  c->h_stage = nullptr;
+  c->d_stage = nullptr;
+  c->stage_cap = 0;
+  const size_t cap = align_up(bytes * 2, 4096);
+  VX_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_stage), cap));
+  VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_stage), cap));
+  c->stage_cap = cap;
+  return VX_OK;
+}
+
+// One batch of <= max_slots frames.  Returns VX_ERR_TABLE_OVERFLOW if a histogram table was too small
+// (caller grows the tables and retries).
+int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
+  int rc = ensure_slots(c, nb);
+  if (rc != VX_OK) return rc;
+
+  // ---- stage the batch description
+  size_t n_items = 0, n_ap = 0, n_ep = 0;
+  for (uint32_t f = 0; f < nb; ++f) {
+    n_items += frames[f].n_prior + frames[f].n_past;
+    n_ap += frames[f].n_prior + frames[f].n_past;
+    n_ep += frames[f].n_endpoints;
+  }
+  const size_t off_items = 0;
+  const size_t off_ap = align_up(off_items + n_items * sizeof(VxFillItem), 256);
+  const size_t off_ep = align_up(off_ap + n_ap * 16 * sizeof(float), 256);
+  const size_t off_vis = align_up(off_ep + n_ep * 3 * sizeof(float), 256);
+  const size_t total = align_up(off_vis + nb * sizeof(VxVisFrame), 256);
+  rc = ensure_stage(c, total);
+  if (rc != VX_OK) return rc;
+  VxFillItem* items = reinterpret_cast<VxFillItem*>(c->h_stage + off_items);
+  float* ap = reinterpret_cast<float*>(c->h_stage + off_ap);
+  float* ep = reinterpret_cast<float*>(c->h_stage + off_ep);
+  VxVisFrame* vis = reinterpret_cast<VxVisFrame*>(c->h_stage + off_vis);
+
+  size_t ii = 0, ai = 0, ei = 0;
+  uint32_t max_points = 0;
+  uint64_t points = 0;
+  for (uint32_t f = 0; f < nb; ++f) {
+    const vx_frame_desc& fr = frames[f];
+    if ((fr.n_prior && (!fr.prior_ids || !fr.ap_prior)) || (fr.n_past && (!fr.past_ids || !fr.ap_past)) || (fr.n_endpoints && !fr.endpoints))
+      return fail(c, VX_ERR_INVALID, "frame descriptor has null arrays");
+    for (int part = 0; part < 2; ++part) {
+      const uint32_t n = part == 0 ? fr.n_prior : fr.n_past;
+      const uint32_t* ids = part == 0 ? fr.prior_ids : fr.past_ids;
+      const float* aps = part == 0 ? fr.ap_prior : fr.ap_past;
+      for (uint32_t s = 0; s < n; ++s) {
+        const auto it = c->scans.find(ids[s]);
+        if (it == c->scans.end()) return fail(c, VX_ERR_UNKNOWN_SCAN, "scan " + std::to_string(ids[s]) + " is not resident");
+        VxFillItem& item = items[ii++];
+        item.points = it->second.points;
+        item.labels = it->second.labels;
+        item.n = it->second.n;
+        item.slot = f;
+        item.ap_index = (uint32_t)ai;
+        item.both = part == 0 ? 1u : 0u;
+        std::memcpy(ap + 16 * ai, aps + 16 * (size_t)s, 16 * sizeof(float));
+        ++ai;
+        if (item.n > max_points) max_points = item.n;
+        points += item.n;
+      }
+    }
+    vis[f].n_endpoints = fr.n_endpoints;
+    vis[f].endpoint_offset = (uint32_t)ei;
+    if (fr.n_endpoints) std::memcpy(ep + 3 * ei, fr.endpoints, (size_t)fr.n_endpoints * 3 * sizeof(float));
+    ei += fr.n_endpoints;
+  }
+
+  cudaStream_t st = c->stream;
+  if (c->tables_dirty) {  // debug mode kept the previous batch's tables
+    VX_CUDA(c, vx_launch_table_reset(c->d_slots, c->dirty_slots, st));
+    c->tables_dirty = false;
+  }
+  VX_CUDA(c, cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, st));
+  VX_CUDA(c, cudaMemsetAsync(c->d_counters, 0, (size_t)nb * kCounterWords * sizeof(uint32_t), st));
+
+  const VxFillItem* d_items = reinterpret_cast<const VxFillItem*>(c->d_stage + off_items);
+  const float* d_ap = reinterpret_cast<const float*>(c->d_stage + off_ap);
+  const float* d_ep = reinterpret_cast<const float*>(c->d_stage + off_ep);
+  const VxVisFrame* d_vis = reinterpret_cast<const VxVisFrame*>(c->d_stage + off_vis);
+
+  VX_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], st));
+  VX_CUDA(c, vx_launch_fill(d_items, (uint32_t)n_items, max_points, d_ap, c->d_slots, c->geom, c->filter, st));
+  VX_CUDA(c, cudaEventRecord(c->ev[EV_FILL], st));
+  VX_CUDA(c, vx_launch_vote(c->d_slots, nb, c->keep_tables ? 1 : 0, st));
+  VX_CUDA(c, cudaEventRecord(c->ev[EV_VOTE], st));
+  VX_CUDA(c, vx_launch_emit(c->d_slots, nb, c->nvox, st));
+  VX_CUDA(c, cudaEventRecord(c->ev[EV_EMIT], st));
+  VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, st));
+  VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS], st));
+  VX_CUDA(c, vx_launch_pack(c->d_slots, nb, c->nvox, st));
+  VX_CUDA(c, cudaEventRecord(c->ev[EV_PACK], st));
+
+  const size_t packed = (size_t)(c->nvox / 8);
+  for (uint32_t f = 0; f < nb; ++f) {
+    const vx_frame_desc& fr = frames[f];
+    const VxSlot& s = c->slots[f].dev;
+    if (fr.out_label) VX_CUDA(c, cudaMemcpyAsync(fr.out_label, s.out_label, (size_t)c->nvox * 2, cudaMemcpyDeviceToHost, st));
+    if (fr.out_bin) VX_CUDA(c, cudaMemcpyAsync(fr.out_bin, s.out_bin, packed, cudaMemcpyDeviceToHost, st));
+    if (fr.out_occluded) VX_CUDA(c, cudaMemcpyAsync(fr.out_occluded, s.out_occluded, packed, cudaMemcpyDeviceToHost, st));
+    if (fr.out_invalid) VX_CUDA(c, cudaMemcpyAsync(fr.out_invalid, s.out_invalid, packed, cudaMemcpyDeviceToHost, st));
+  }
+  VX_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, (size_t)nb * kCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  VX_CUDA(c, cudaEventRecord(c->ev[EV_END], st));
+  VX_CUDA(c, cudaStreamSynchronize(st));
+  if (c->keep_tables) {
+    c->tables_dirty = true;
+    c->dirty_slots = nb;
+  }
+  c->last_batch = nb;
+
+  bool overflow = false;
+  uint64_t rays = 0, steps = 0;
+  for (uint32_t f = 0; f < nb; ++f) {
+    const uint32_t* w = c->h_counters + (size_t)f * kCounterWords;
+    if (w[1] || w[3]) overflow = true;
+    unsigned long long rs[2];
+    std::memcpy(rs, w + 4, sizeof(rs));
+    rays += rs[0];
+    steps += rs[1];
+  }
+  if (overflow) return VX_ERR_TABLE_OVERFLOW;
+
+  float ms = 0;
+  auto span = [&](int a, int b) {
+    cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]);
+    return (double)ms;
+  };
+  c->times.fill_ms += span(EV_BEGIN, EV_FILL);
+  c->times.vote_ms += span(EV_FILL, EV_VOTE);
+  c->times.emit_ms += span(EV_VOTE, EV_EMIT);
+  c->times.visibility_ms += span(EV_EMIT, EV_VIS);
+  c->times.pack_ms += span(EV_VIS, EV_PACK);
+  c->times.total_ms += span(EV_BEGIN, EV_END);
+  c->times.frames += nb;
+  c->times.points_read += points;
+  c->times.fill_launches += (n_items + 65534) / 65535;
+  c->times.vote_launches += 1;
+  c->times.emit_launches += 1;
+  c->times.visibility_launches += 1;
+  c->times.pack_launches += 1;
+  c->times.rays_cast += rays;
+  c->times.dda_steps += steps;
+  return VX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vx_last_global_error(void) { return g_global_error.c_str(); }
+const char* vx_last_error(const vx_ctx* ctx) { return ctx ? ctx->error.c_str() : g_global_error.c_str(); }
+
+int vx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void* vx_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void vx_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter, const vx_options* options, vx_ctx** out) {
+  if (!grid || !filter || !out) return fail(nullptr, VX_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, VX_ERR_NO_DEVICE, "no CUDA device: voxelizer_b200 has no CPU path");
+  if (device < 0 || device >= ndev) return fail(nullptr, VX_ERR_INVALID, "device index out of range");
+  if (!(grid->resolution > 0.0f)) return fail(nullptr, VX_ERR_INVALID, "resolution must be positive");
+
+  vx_ctx* c = new vx_ctx;
+  auto bail = [&](int code) {
+    g_global_error = c->error;
+    vx_destroy(c);
+    return code;
+  };
+#define VX_CREATE_CUDA(call)                                                          \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      c->error = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+      return bail(VX_ERR_CUDA);                                                       \
+    }                                                                                 \
+  } while (0)
+
+  c->device = device;
+  VX_CREATE_CUDA(cudaSetDevice(device));
+  VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < EV_COUNT; ++i) VX_CREATE_CUDA(cudaEventCreate(&c->ev[i]));
+  VX_CREATE_CUDA(vx_visibility_prepare());
+
+  derive_geometry(*grid, c->geom);
+  std::memcpy(c->min_extent, grid->min_extent, sizeof(c->min_extent));
+  std::memcpy(c->max_extent, grid->max_extent, sizeof(c->max_extent));
+  if (c->geom.nx <= 0 || c->geom.ny <= 0 || c->geom.nz <= 0) {
+    c->error = "empty grid";
+    return bail(VX_ERR_INVALID);
+  }
+  c->nvox = (uint64_t)c->geom.nx * (uint64_t)c->geom.ny * (uint64_t)c->geom.nz;
+  if (c->nvox >= (1ull << 31) || vx_visibility_visits(c->geom) >= (1ull << 25)) {
+    c->error = "grid too large: the traversal's visit counter has 25 bits";
+    return bail(VX_ERR_UNSUPPORTED);
+  }
+  c->words = (uint32_t)((c->nvox + 31) / 32);
+
+  // label filter LUT (voxelize_utils.cpp:175-180,195-198): label -> joined label -> in `ignore`?
+  c->filter.min_range = filter->min_range;
+  c->filter.max_range = filter->max_range;
+  c->filter.hidecar = filter->hidecar ? 1 : 0;
+  c->filter.has_label_filter = filter->n_filtered > 0 ? 1 : 0;
+  {
+    std::map<uint32_t, uint32_t> member_to_key;  // later keys overwrite earlier ones, as in the reference
+    for (uint32_t i = 0; i < filter->n_join_pairs; ++i) member_to_key[filter->join_pairs[2 * i + 1]] = filter->join_pairs[2 * i];
+    std::vector<uint32_t> bits(65536 / 32, 0);
+    for (uint32_t label = 0; label < 65536; ++label) {
+      uint32_t mapped = label;
+      const auto it = member_to_key.find(label);
+      if (it != member_to_key.end()) mapped = it->second;
+      bool rejected = false;
+      for (uint32_t i = 0; i < filter->n_filtered; ++i) rejected |= filter->filtered_labels[i] == mapped;
+      if (rejected) bits[label >> 5] |= 1u << (label & 31);
+    }
+    VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_reject_bits), bits.size() * 4));
+    VX_CREATE_CUDA(cudaMemcpy(c->d_reject_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    c->filter.reject_bits = c->d_reject_bits;
+  }
+
+  if (options) {
+    if (options->table_log2_capacity) c->log2_target = options->table_log2_capacity;
+    c->keep_tables = (options->reserved[0] & 1u) != 0;
+  }
+  if (c->log2_target < 10) c->log2_target = 10;
+  if (c->log2_target > 30) c->log2_target = 30;
+  c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
+
+  size_t free_b = 0, total_b = 0;
+  VX_CREATE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  uint32_t want = options && options->frames_in_flight ? options->frames_in_flight : 296u;
+  const size_t per_slot = slot_bytes(c);
+  const size_t budget = free_b / 2;
+  if ((size_t)want * per_slot > budget) want = (uint32_t)(budget / per_slot);
+  if (want < 1) want = 1;
+  c->max_slots = want;
+  VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_slots), (size_t)want * sizeof(VxSlot)));
+  VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_counters), (size_t)want * kCounterWords * sizeof(uint32_t)));
+  VX_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_counters), (size_t)want * kCounterWords * sizeof(uint32_t)));
+#undef VX_CREATE_CUDA
+  *out = c;
+  return VX_OK;
+}
+
+void vx_destroy(vx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_slots(c);
+  for (auto& kv : c->scans) {
+    cudaFree(kv.second.points);
+    cudaFree(kv.second.labels);
+  }
+  if (c->d_slots) cudaFree(c->d_slots);
+  if (c->d_counters) cudaFree(c->d_counters);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->d_reject_bits) cudaFree(c->d_reject_bits);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->d_stage) cudaFree(c->d_stage);
+  for (int i = 0; i < EV_COUNT; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int vx_grid_info_get(const vx_ctx* c, vx_grid_info* out) {
+  if (!c || !out) return VX_ERR_INVALID;
+  out->size[0] = (uint32_t)c->geom.nx;
+  out->size[1] = (uint32_t)c->geom.ny;
+  out->size[2] = (uint32_t)c->geom.nz;
+  out->offset[0] = c->geom.off[0];
+  out->offset[1] = c->geom.off[1];
+  out->offset[2] = c->geom.off[2];
+  out->resolution = c->geom.res;
+  out->num_voxels = c->nvox;
+  out->packed_bytes = c->nvox / 8;
+  out->label_bytes = c->nvox * 2;
+  return VX_OK;
+}
+
+uint32_t vx_frames_in_flight(const vx_ctx* c) { return c ? c->max_slots : 0; }
+
+int vx_upload_scan(vx_ctx* c, uint32_t scan_id, const float* xyzr, const uint32_t* labels, uint32_t n) {
+  if (!c || (n && (!xyzr || !labels))) return fail(c, VX_ERR_INVALID, "null argument");
+  VX_CUDA(c, cudaSetDevice(c->device));
+  vx_evict_scan(c, scan_id);
+  DeviceScan s;
+  s.n = n;
+  if (n) {
+    VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&s.points), (size_t)n * sizeof(float4)));
+    VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&s.labels), (size_t)n * sizeof(uint32_t)));
+    VX_CUDA(c, cudaMemcpyAsync(s.points, xyzr, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(c, cudaMemcpyAsync(s.labels, labels, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  c->scans[scan_id] = s;
+  return VX_OK;
+}
+
+int vx_evict_scan(vx_ctx* c, uint32_t scan_id) {
+  if (!c) return VX_ERR_INVALID;
+  const auto it = c->scans.find(scan_id);
+  if (it == c->scans.end()) return VX_OK;
+  cudaFree(it->second.points);
+  cudaFree(it->second.labels);
+  c->scans.erase(it);
+  return VX_OK;
+}
+
+int vx_evict_all(vx_ctx* c) {
+  if (!c) return VX_ERR_INVALID;
+  for (auto& kv : c->scans) {
+    cudaFree(kv.second.points);
+    cudaFree(kv.second.labels);
+  }
+  c->scans.clear();
+  return VX_OK;
+}
+
+int vx_process_frames(vx_ctx* c, const vx_frame_desc* frames, uint32_t n) {
+  if (!c || (n && !frames)) return fail(c, VX_ERR_INVALID, "null argument");
+  VX_CUDA(c, cudaSetDevice(c->device));
+  for (uint32_t base = 0; base < n;) {
+    const uint32_t nb = n - base < c->max_slots ? n - base : c->max_slots;
+    int rc = run_batch(c, frames + base, nb);
+    if (rc == VX_ERR_TABLE_OVERFLOW) {
+      // grow the histogram tables (x4) and redo this batch
+      if (c->log2_target >= 28) return fail(c, VX_ERR_TABLE_OVERFLOW, "histogram table overflow at 2^28 slots");
+      VX_CUDA(c, cudaStreamSynchronize(c->stream));
+      free_slots(c);
+      c->log2_target += 2;
+      c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
+      const size_t per_slot = slot_bytes(c);
+      size_t free_b = 0, total_b = 0;
+      VX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+      uint32_t fit = (uint32_t)((free_b / 2) / per_slot);
+      if (fit < 1) fit = 1;
+      if (fit < c->max_slots) c->max_slots = fit;
+      continue;
+    }
+    if (rc != VX_OK) return rc;
+    base += nb;
+  }
+  return VX_OK;
+}
+
+int vx_sync(vx_ctx* c) {
+  if (!c) return VX_ERR_INVALID;
+  VX_CUDA(c, cudaSetDevice(c->device));
+  VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VX_OK;
+}
+
+int vx_stage_times_get(vx_ctx* c, vx_stage_times* out) {
+  if (!c || !out) return VX_ERR_INVALID;
+  *out = c->times;
+  return VX_OK;
+}
+
+int vx_stage_times_reset(vx_ctx* c) {
+  if (!c) return VX_ERR_INVALID;
+  c->times = vx_stage_times{};
+  return VX_OK;
+}
+
+int vx_debug_dump(vx_ctx* c, uint32_t frame_index, int kind, void* dst, uint64_t* count) {
+  if (!c || !count) return fail(c, VX_ERR_INVALID, "null argument");
+  if (frame_index >= c->last_batch) return fail(c, VX_ERR_INVALID, "frame index outside the last batch");
+  VX_CUDA(c, cudaSetDevice(c->device));
+  const VxSlot& s = c->slots[frame_index].dev;
+  if (kind == VX_DUMP_HIST_TARGET || kind == VX_DUMP_HIST_INPUT) {
+    if (!c->keep_tables || !c->tables_dirty) return fail(c, VX_ERR_INVALID, "histogram dump needs vx_options.reserved[0] = 1");
+    const VxTable& t = kind == VX_DUMP_HIST_TARGET ? s.target : s.input;
+    uint32_t used = 0;
+    VX_CUDA(c, cudaMemcpy(&used, t.used_count, 4, cudaMemcpyDeviceToHost));
+    *count = used;
+    if (!dst || used == 0) return VX_OK;
+    const size_t cap = (size_t)1 << t.log2_cap;
+    std::vector<uint32_t> idx(used);
+    std::vector<unsigned long long> keys(cap);
+    std::vector<uint32_t> counts(cap);
+    VX_CUDA(c, cudaMemcpy(idx.data(), t.used, (size_t)used * 4, cudaMemcpyDeviceToHost));
+    VX_CUDA(c, cudaMemcpy(keys.data(), t.keys, cap * 8, cudaMemcpyDeviceToHost));
+    VX_CUDA(c, cudaMemcpy(counts.data(), t.counts, cap * 4, cudaMemcpyDeviceToHost));
+    uint32_t* o = static_cast<uint32_t*>(dst);
+    for (uint32_t u = 0; u < used; ++u) {
+      const unsigned long long k = keys[idx[u]];
+      o[3 * (size_t)u + 0] = (uint32_t)(k >> 16);
+      o[3 * (size_t)u + 1] = (uint32_t)(k & 0xFFFFull);
+      o[3 * (size_t)u + 2] = counts[idx[u]];
+    }
+    return VX_OK;
+  }
+  if (kind == VX_DUMP_OCCUPANCY || kind == VX_DUMP_OCCLUDED || kind == VX_DUMP_INVALID) {
+    *count = c->nvox;
+    if (!dst) return VX_OK;
+    std::vector<uint32_t> a(c->words), b(c->words);
+    const uint32_t* src = kind == VX_DUMP_OCCUPANCY ? s.occ : (kind == VX_DUMP_OCCLUDED ? s.occl : s.alive);
+    VX_CUDA(c, cudaMemcpy(a.data(), src, (size_t)c->words * 4, cudaMemcpyDeviceToHost));
+    if (kind == VX_DUMP_INVALID) {
+      VX_CUDA(c, cudaMemcpy(b.data(), s.occ, (size_t)c->words * 4, cudaMemcpyDeviceToHost));
+      for (uint32_t w = 0; w < c->words; ++w) a[w] &= ~b[w];
+    }
+    uint8_t* o = static_cast<uint8_t*>(dst);
+    for (uint64_t L = 0; L < c->nvox; ++L) o[L] = (a[L >> 5] >> (L & 31)) & 1u;
+    return VX_OK;
+  }
+  return fail(c, VX_ERR_INVALID, "unknown dump kind");
+}
+
+}  // extern "C"

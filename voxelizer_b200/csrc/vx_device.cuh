@@ -1,0 +1,71 @@
+// Device-side data layout shared by the kernels of the gen_data hot path.
+//
+// Device voxel index = the OUTPUT order of saveVoxelGrid (voxelize_utils.cpp:229-255):
+//   L = (x * Sy + y) * Sz + z      (z fastest)
+// so `.label` is the dense label array as is, the bit-packers write consecutive words, and with
+// Sz = 32 one (x,y) column is one 32-bit word of every bitmap.  The reference's internal x-fastest
+// index (VoxelGrid.h:117) never exists on the device; only its visit ORDER does (vx_visibility.cu).
+#ifndef VOXELIZER_B200_VX_DEVICE_CUH_
+#define VOXELIZER_B200_VX_DEVICE_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vx_dda.h"
+
+#define VX_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define VX_MAX_PROBES 4096u
+
+// Open-addressing histogram of one grid of one frame: (L << 16 | label16) -> count.
+struct VxTable {
+  unsigned long long* keys;  // [cap], VX_EMPTY_KEY when free
+  uint32_t* counts;          // [cap]
+  uint32_t* used;            // [cap] slots claimed this frame (for O(used) vote + reset)
+  uint32_t* used_count;      // [1]
+  uint32_t* overflow;        // [1] set when a probe sequence ran out
+  uint32_t log2_cap;
+};
+
+// One frame slot: everything a frame in flight needs on the device.
+struct VxSlot {
+  VxTable input;              // priorGrid histogram
+  VxTable target;             // pastGrid histogram
+  unsigned long long* best_input;   // [nvox] count << 16 | (0xFFFF - label), 0 = empty voxel
+  unsigned long long* best_target;  // [nvox]
+  uint32_t* occ;              // [words] target grid occupancy (count > 0), bit L
+  uint32_t* occl;             // [words] occlusions_ > -1
+  uint32_t* alive;            // [words] invalid_ != -1
+  uint32_t* memo;             // [nvox]  occludedBy_ as (epoch << 26 | tau << 1 | hit)
+  uint16_t* out_label;        // [nvox]
+  uint32_t* out_bin;          // [words] MSB-first packed
+  uint32_t* out_occluded;     // [words]
+  uint32_t* out_invalid;      // [words]
+  unsigned long long* counters;  // [2] rays, steps (statistics)
+};
+
+// One (frame, scan) unit of fill work.
+struct VxFillItem {
+  const float4* points;
+  const uint32_t* labels;
+  uint32_t n;
+  uint32_t slot;
+  uint32_t ap_index;  // into the batch's ap array (16 floats each)
+  uint32_t both;      // 1: prior scan -> input AND target grid; 0: past scan -> target only
+};
+
+struct VxFilterDev {
+  float min_range, max_range;
+  int32_t hidecar;
+  int32_t has_label_filter;
+  const uint32_t* reject_bits;  // 65536-bit LUT over the (masked) label: joined label is in `ignore`
+};
+
+// Per-frame visibility work.
+struct VxVisFrame {
+  uint32_t n_endpoints;
+  uint32_t endpoint_offset;  // into the batch's endpoint array (3 floats each)
+};
+
+__device__ __forceinline__ uint32_t vx_ldcg_u32(const uint32_t* p) { return __ldcg(p); }
+
+#endif

@@ -1,0 +1,28 @@
+// Host-callable launch wrappers of the kernels (defined in vx_fill.cu / vx_visibility.cu).
+#ifndef VOXELIZER_B200_VX_LAUNCH_H_
+#define VOXELIZER_B200_VX_LAUNCH_H_
+
+#include "vx_device.cuh"
+
+// K1+K2: transform + filter + voxel key + (voxel,label) histogram insert.  grid = (tiles, items).
+cudaError_t vx_launch_fill(const VxFillItem* items, uint32_t n_items, uint32_t max_points, const float* ap,
+                           const VxSlot* slots, VxGridGeom geom, VxFilterDev filter, cudaStream_t stream);
+
+// K3: per-voxel majority vote over the used histogram slots (also frees them unless keep_tables).
+cudaError_t vx_launch_vote(const VxSlot* slots, uint32_t n_slots, int keep_tables, cudaStream_t stream);
+// Frees the used slots of tables that were kept for debugging.
+cudaError_t vx_launch_table_reset(const VxSlot* slots, uint32_t n_slots, cudaStream_t stream);
+
+// K5a: best -> .label (uint16), .bin (packed, input grid), occupancy bitmap; clears `best`.
+cudaError_t vx_launch_emit(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, cudaStream_t stream);
+
+// K4: occlusion pass + invalid passes, one CTA per frame.
+cudaError_t vx_visibility_prepare();  // opt-in to large dynamic shared memory (once per process)
+cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, uint32_t n_slots,
+                                 const float* endpoints, VxGridGeom geom, cudaStream_t stream);
+uint64_t vx_visibility_visits(VxGridGeom geom);  // visits per pass (must stay < 2^25)
+
+// K5b: occl / alive bitmaps -> MSB-first packed .occluded / .invalid.
+cudaError_t vx_launch_pack(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, cudaStream_t stream);
+
+#endif
