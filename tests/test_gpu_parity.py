@@ -1,0 +1,197 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs -- bit-exact (integer / byte / index work; the fp32 voxel index must match exactly too)."""
+import os
+
+import numpy as np
+import pytest
+
+import voxelizer_b200 as vx
+from frames import assert_frames_equal, oracle_frame, product_frame
+from oracle.oracle import Oracle, have_ref
+from util import cfg_path, compare_dirs, load_scan, make_sequence
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle("port")
+
+
+def _load_sequence(seq):
+    cnt, poses = vx.read_poses(seq)
+    scans, labels = zip(*[load_scan(seq, t) for t in range(cnt)])
+    return cnt, poses, list(scans), [l & 0xFFFF for l in labels], list(labels)
+
+
+def _backend(cfg_name, scans, raw_labels, **kw):
+    be = vx.Backend.from_config(vx.Config(cfg_path(cfg_name)), debug=True, **kw)
+    for t, (s, l) in enumerate(zip(scans, raw_labels)):
+        be.upload_scan(t, s, l)  # raw labels: the library applies & 0xFFFF like the reader
+    return be
+
+
+@pytest.mark.parametrize("cfg_name,n,beams,az", [("test_small", 10, 16, 300), ("example", 8, 32, 500), ("settings", 5, 32, 600),
+                                                  ("semantic_kitti", 7, 64, 1200)])
+def test_frame_internals(orc, tmp_path, cfg_name, n, beams, az):
+    """histograms, majority labels, occupancy, occlusions_, invalid_ and the packed outputs of single frames."""
+    seq = make_sequence(str(tmp_path / "seq"), n, beams, az)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    cfg = vx.Config(cfg_path(cfg_name))
+    be = _backend(cfg_name, scans, raw)
+    for target in (0, cnt // 2, cnt - 1):  # cnt-1: the last scan is its own past window
+        pb, pe, qb, qe = vx.window(cnt, cfg.pod.priorScans, cfg.pod.pastScans, target)
+        prior, past = list(range(pb, pe)), list(range(qb, qe))
+        o = oracle_frame(orc, cfg_path(cfg_name), scans, labels, poses, prior, past)
+        p = product_frame(be, poses, prior, past)
+        assert be.size == tuple(o["size"]) and np.array_equal(be.offset.view(np.uint32), np.asarray(o["offset"], np.float32).view(np.uint32))
+        assert np.array_equal(p["endpoints"].view(np.uint32), o["endpoints"].view(np.uint32))
+        assert_frames_equal(p, o)
+    be.close()
+
+
+def test_adversarial_points(orc):
+    """Boundary ranges, voxel faces, NaN / inf, label ties, majority label 0, instance bits, empty scans."""
+    cfg_name = "test_small"  # min range 2.5, max range 40, ignore [0, 30], join {0:[1]}, {10:[252,13]}; res 0.8
+    rng = np.random.default_rng(1)
+    pts = []
+    # exactly at the range limits (kept: the reference rejects only range < min or > max)
+    for r in (2.5, np.nextafter(np.float32(2.5), 0), np.nextafter(np.float32(2.5), 9), 40.0, np.nextafter(np.float32(40), 99)):
+        pts += [(0, float(r), 0, 0.5), (float(r) * 0.6, float(r) * 0.8, 0, 0.5)]
+    # ego-vehicle box borders
+    pts += [(3.0, 0.5, 1, 0), (2.9999, 1.9999, 1, 0), (-2.0, 0.0, 3.5, 0), (-1.99, 2.0, 3.5, 0), (2.5, -2.0, 4.0, 0), (4.0, 0.1, 0, 0)]
+    # voxel faces of the 0.8 m grid (offset (0,-12.8,-2)) and grid borders
+    for v in (0.8, 1.6, 2.4000000954, 3.2, 25.6, 25.599998, 12.8, -12.8, 4.4, -2.0, 0.0, -0.0):
+        pts += [(v, 3.0, 0.3, 0), (5.0, v, 0.3, 0), (5.0, 3.0, v, 0)]
+    pts += [(np.nan, 5, 0, 0), (5, np.inf, 0, 0), (-np.inf, 5, 0, 0), (3e9, 5, 5, 0), (1e38, 1e38, 1e38, 0), (5, 5, np.nan, 0)]
+    pts = np.array(pts, np.float32)
+    lab = (rng.integers(0, 6, len(pts)) * 10).astype(np.uint32)
+    # ties / majority label 0 / ignored + joined labels / instance bits in one voxel cluster at (6.0..6.7, 4.0..4.7, 0.5)
+    cluster = [((6.1, 4.1, 0.5, 0), 40), ((6.2, 4.2, 0.5, 0), 50), ((6.3, 4.3, 0.5, 0), 50), ((6.4, 4.4, 0.5, 0), 40),   # tie 40/50 -> 40
+               ((7.0, 4.1, 0.5, 0), 1), ((7.1, 4.2, 0.5, 0), 13), ((7.2, 4.3, 0.5, 0), 252), ((7.3, 4.2, 0.5, 0), 30),  # 1->0 ignored, 13/252->10 kept as 13/252, 30 ignored
+               ((8.1, 4.1, 0.5, 0), 2), ((8.2, 4.1, 0.5, 0), 2), ((8.3, 4.1, 0.5, 0), 0x70002), ((8.4, 4.1, 0.5, 0), 0xFFFF0030)]  # instance bits
+    pts = np.vstack([pts, np.array([c[0] for c in cluster], np.float32)])
+    lab = np.concatenate([lab, np.array([c[1] for c in cluster], np.uint32)])
+    scans = [pts, np.zeros((0, 4), np.float32), pts[::-1].copy() + np.float32([0.37, -0.21, 0.05, 0])]
+    raw = [lab, np.zeros(0, np.uint32), lab[::-1].copy()]
+    labels = [l & 0xFFFF for l in raw]
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    shift = np.eye(4, dtype=np.float32)
+    shift[:3, 3] = (1.25, -0.5, 0.1)
+    poses = np.stack([ident, shift.T.reshape(16), ident])
+    be = _backend(cfg_name, scans, raw)
+    for prior, past in (([0], [1, 2]), ([0, 1], [2]), ([1], [1]), ([2], [])):
+        o = oracle_frame(orc, cfg_path(cfg_name), scans, labels, poses, prior, past)
+        p = product_frame(be, poses, prior, past)
+        assert_frames_equal(p, o)
+    be.close()
+
+
+def test_endpoints_everywhere(orc, tmp_path):
+    """updateInvalid with endpoints outside the grid, on voxel centres / faces / corners and at the origin."""
+    seq = make_sequence(str(tmp_path / "seq"), 3, 32, 500)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    for cfg_name in ("example", "test_small"):
+        be = _backend(cfg_name, scans, raw)
+        res, off = float(be.resolution), be.offset.astype(np.float64)
+        sx, sy, sz = be.size
+        eps = [(0, 0, 0), (70, 3, 1), (-5, -30, 9), (1e4, 1e4, 1e4), tuple(off + res * np.array([3.5, 2.5, 1.5])), tuple(off + res * np.array([4, 4, 2])),
+               tuple(off), tuple(off + res * np.array([sx, sy, sz])), tuple(off + res * np.array([sx - 0.5, 0.5, sz - 0.5])), (12.3, -4.56, 0.789),
+               (20, 0, -1.9999), (0.0001, 0.0001, 0.0001)]
+        eps = np.array(eps, np.float32)
+        o = oracle_frame(orc, cfg_path(cfg_name), scans, labels, poses, [0], [1, 2], extra_endpoints=eps)
+        p = product_frame(be, poses, [0], [1, 2], extra_endpoints=eps)
+        assert_frames_equal(p, o)
+        be.close()
+
+
+def test_random_occupancy_visibility(orc):
+    """Dense random occupancy on odd-sized grids: stresses in-wave resolution and the multi-word columns."""
+    rng = np.random.default_rng(9)
+    for (mn, mx, res), dens in ((((0, -4, -1), (8, 4, 1), 0.5), 0.2), (((-3, -2, -1), (5, 7, 2.5), 0.5), 0.05), (((0, -3, 0), (4, 3, 8), 1.0), 0.3),
+                                (((0, -10, -2), (20, 10, 4.6), 0.3), 0.02)):
+        g = orc.grid(res, mn, mx)
+        n = int(g.nvox * dens) + 1
+        pts = np.column_stack([rng.uniform(mn[a], mx[a], n) for a in range(3)] + [np.zeros(n)]).astype(np.float32)
+        lab = rng.integers(1, 5, n).astype(np.uint32)
+        eps = np.column_stack([rng.uniform(mn[a] - 2, mx[a] + 2, 7) for a in range(3)]).astype(np.float32)
+        be = vx.Backend(res, mn, mx, 0.0, 1e9, hidecar=False, debug=True)
+        be.upload_scan(0, pts, lab)
+        ident = np.eye(4, dtype=np.float32).reshape(1, 16)
+        spec = vx.FrameSpec(np.array([0], np.uint32), ident, np.zeros(0, np.uint32), np.zeros((0, 16), np.float32), eps)
+        out = be.process([spec])[0]
+        g.insert(np.column_stack([pts[:, :3], np.ones(n, np.float32)]), lab)
+        g.update_occlusions()
+        for e in eps:
+            g.update_invalid(e)
+        occl, inv = g.flags()
+        assert np.array_equal(be.dump(0, vx.DUMP_OCCLUDED), occl)
+        assert np.array_equal(be.dump(0, vx.DUMP_INVALID), inv)
+        be.close()
+
+
+@pytest.mark.parametrize("cfg_name,n,beams,az", [("test_small", 17, 16, 300), ("example", 12, 32, 600), ("semantic_kitti", 11, 64, 2000),
+                                                  ("semantic_kitti_dense", 4, 64, 1000)])
+def test_gen_data_whole_program(orc, tmp_path, cfg_name, n, beams, az):
+    """vx_gen_data's files == the oracle's gen_data files (file list and bytes)."""
+    seq = make_sequence(str(tmp_path / "seq"), n, beams, az)
+    orc.gen_data(cfg_path(cfg_name), seq, str(tmp_path / "oracle"))
+    st = vx.gen_data(cfg_path(cfg_name), seq, str(tmp_path / "gpu"))
+    assert compare_dirs(str(tmp_path / "gpu"), str(tmp_path / "oracle")) == []
+    assert st["frames"] * 4 == len(os.listdir(tmp_path / "oracle"))
+    if have_ref():  # the reference binary itself travelled with the snapshot
+        Oracle("ref").gen_data(cfg_path(cfg_name), seq, str(tmp_path / "ref"))
+        assert compare_dirs(str(tmp_path / "gpu"), str(tmp_path / "ref")) == []
+
+
+def test_gen_data_executable(orc, tmp_path):
+    """The drop-in executable, with the reference's positional arguments."""
+    import subprocess
+    seq = make_sequence(str(tmp_path / "seq"), 9, 16, 300)
+    orc.gen_data(cfg_path("test_small"), seq, str(tmp_path / "oracle"))
+    subprocess.check_call([vx.GEN_DATA_EXE, cfg_path("test_small"), seq, str(tmp_path / "gpu"), "--quiet"])
+    assert compare_dirs(str(tmp_path / "gpu"), str(tmp_path / "oracle")) == []
+
+
+def test_size_independent_properties(tmp_path):
+    """Full-size grid (256x256x32): batch size, sharding and repetition do not change a byte; set relations
+    between the four products hold."""
+    seq = make_sequence(str(tmp_path / "seq"), 16, 64, 2000)
+    cfg = cfg_path("semantic_kitti_dense")
+    a = vx.gen_data(cfg, seq, str(tmp_path / "a"))
+    vx.gen_data(cfg, seq, str(tmp_path / "b"), frames_in_flight=3)
+    vx.gen_data(cfg, seq, str(tmp_path / "c"), shard=(0, 2))
+    vx.gen_data(cfg, seq, str(tmp_path / "c"), shard=(1, 2))
+    assert a["frames"] == 16
+    assert compare_dirs(str(tmp_path / "a"), str(tmp_path / "b")) == []
+    assert compare_dirs(str(tmp_path / "a"), str(tmp_path / "c")) == []
+    for t in (0, 7, 15):
+        rd = lambda ext, dt: np.fromfile(str(tmp_path / "a" / f"{t:06d}.{ext}"), dt)
+        label = rd("label", np.uint16)
+        unpack = lambda ext: np.unpackbits(rd(ext, np.uint8), bitorder="big").astype(bool)
+        b, occl, inv = unpack("bin"), unpack("occluded"), unpack("invalid")
+        assert label.size == 256 * 256 * 32 and b.size == label.size
+        assert not (inv & (label > 0)).any()      # labelled voxels are occupied, occupied voxels are never invalid
+        assert not (inv & ~occl).any()            # invalid implies occluded from the origin
+        assert ((label > 0) <= occl).all()        # occupied voxels count as occluded
+        assert (b <= occl).all()                  # the target scan's own voxels are occupied in the target grid
+
+
+def test_table_growth_is_transparent(orc, tmp_path):
+    """A histogram table that is far too small overflows, is grown and the frame redone -- same bytes."""
+    seq = make_sequence(str(tmp_path / "seq"), 5, 32, 600)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    be = _backend("example", scans, raw, table_log2_capacity=10)
+    o = oracle_frame(orc, cfg_path("example"), scans, labels, poses, [0], [1, 2, 3, 4])
+    p = product_frame(be, poses, [0], [1, 2, 3, 4])
+    assert_frames_equal(p, o, what=("label", "bin", "occupancy", "occluded", "invalid", "occluded_packed", "invalid_packed"))
+    be.close()
+
+
+def test_unknown_scan_is_an_error():
+    be = vx.Backend(0.5, (0, -4, -1), (8, 4, 1), 2.5, 25.0)
+    ident = np.eye(4, dtype=np.float32).reshape(1, 16)
+    spec = vx.FrameSpec(np.array([7], np.uint32), ident, np.zeros(0, np.uint32), np.zeros((0, 16), np.float32), np.zeros((0, 3), np.float32))
+    with pytest.raises(vx.VxError, match="not resident"):
+        be.process([spec])
+    be.close()

@@ -1,0 +1,51 @@
+"""The CPU model of the GPU visibility algorithm (tests/model/wave_model.cpp: waves in reference visit
+order, snapshot / resolve / trace / apply, order-scrambled merges) against the oracle, bit for bit."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_model(grid, occ_out, endpoints, wave_cells=4096, seed=1):
+    wm = C.CDLL(os.path.join(HERE, "model", "libwave_model.so"))
+    size = np.array(grid.size, np.int32)
+    off = np.ascontiguousarray(grid.offset, np.float32)
+    occ = np.ascontiguousarray(occ_out, np.uint8)
+    ep = np.ascontiguousarray(endpoints, np.float32).reshape(-1, 3)
+    o = np.zeros(grid.nvox, np.uint8)
+    iv = np.zeros(grid.nvox, np.uint8)
+    st = np.zeros(8, np.uint64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    wm.wm_run(p(size), C.c_float(float(grid.resolution)), p(off), p(occ), C.c_uint32(len(ep)), p(ep), C.c_uint32(wave_cells),
+              C.c_uint64(seed), p(o), p(iv), p(st))
+    return o, iv, st
+
+
+@pytest.mark.parametrize("shape", [((0, -4, -1), (8, 4, 1), 0.5), ((0, -20, -2), (40, 20, 1), 0.6), ((-3, -2, -1), (5, 7, 2.5), 0.5),
+                                   ((0, -3, 0), (4, 3, 8), 1.0)])
+@pytest.mark.parametrize("dens", [0.002, 0.03, 0.25])
+def test_wave_model_matches_oracle(shape, dens):
+    orc = Oracle("port")
+    mn, mx, res = shape
+    rng = np.random.default_rng(int(dens * 1000) + len(str(shape)))
+    g = orc.grid(res, mn, mx)
+    n = int(g.nvox * dens) + 1
+    pts = np.column_stack([rng.uniform(mn[a] - 0.5, mx[a] + 0.5, n) for a in range(3)] + [np.ones(n)]).astype(np.float32)
+    eps = np.column_stack([rng.uniform(mn[a] - 2, mx[a] + 2, 6) for a in range(3)]).astype(np.float32)
+    eps[0] = 0
+    eps[1] = g.offset + np.float32(res) * np.array([3, 2, 1], np.float32) + np.float32(res * 0.5)
+    g.insert(pts, np.ones(n, np.uint32))
+    g.update_occlusions()
+    for e in eps:
+        g.update_invalid(e)
+    occ_f, inv_f = g.flags()
+    occb = (g.to_output_order(g.counts()) > 0).astype(np.uint8)
+    for wave_cells in (4096, 64, 1):
+        o, iv, st = run_model(g, occb, eps, wave_cells, seed=wave_cells + 3)
+        assert st[7] == 0, "a visited cell had no memo"
+        assert np.array_equal(o, occ_f) and np.array_equal(iv, inv_f), (wave_cells, int((o != occ_f).sum()), int((iv != inv_f).sum()))

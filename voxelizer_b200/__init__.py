@@ -3,7 +3,7 @@
 Python is only a binding here: the product is the C ABI in ``include/voxelizer_b200.h`` (CUDA kernels
 for sm_100a in ``csrc/``) plus the C++ host layer in ``host/`` that mirrors the reference's own API.
 This module loads the in-tree shared libraries with ctypes.  If the CUDA library is missing it raises --
-there is no CPU fallback and nothing here ever imports ``oracle/``.
+there is no CPU fallback, and the CPU checker used by the tests is never imported from here.
 """
 from __future__ import annotations
 
@@ -48,7 +48,8 @@ class FilterDesc(C.Structure):
 
 
 class Options(C.Structure):
-    _fields_ = [("frames_in_flight", C.c_uint32), ("table_log2_capacity", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+    _fields_ = [("frames_in_flight", C.c_uint32), ("table_log2_capacity", C.c_uint32), ("stream", C.c_void_p),
+                ("debug", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class FrameDesc(C.Structure):
@@ -186,6 +187,8 @@ def synth_lib():
         L.vxs_scan.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
         L.vxs_velo_pose.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_void_p]
         L.vxs_calib_tr.argtypes = [C.c_void_p]
+        L.vxs_generate_many.restype = C.c_int
+        L.vxs_generate_many.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
         L.vxs_write_sequence.restype = C.c_int
         L.vxs_write_sequence.argtypes = [C.POINTER(SynthParams), C.c_char_p, C.c_uint32, C.c_int, C.c_int]
         _synth = L
@@ -347,7 +350,7 @@ class Backend:
     """One vx_ctx (one GPU)."""
 
     def __init__(self, resolution, min_extent, max_extent, min_range, max_range, hidecar=True, filtered=(), join_pairs=(),
-                 device: int = 0, frames_in_flight: int = 0, table_log2_capacity: int = 0, debug: bool = False):
+                 device: int = 0, frames_in_flight: int = 0, table_log2_capacity: int = 0, debug: bool = False, stream: int = 0):
         L = cuda_lib()
         gd = GridDesc(resolution=float(resolution))
         for a in range(3):
@@ -358,8 +361,8 @@ class Backend:
         fd = FilterDesc(min_range=float(min_range), max_range=float(max_range), hidecar=int(bool(hidecar)),
                         filtered_labels=self._filtered.ctypes.data if len(self._filtered) else None, n_filtered=len(self._filtered),
                         join_pairs=self._joins.ctypes.data if len(self._joins) else None, n_join_pairs=len(self._joins) // 2)
-        op = Options(frames_in_flight=frames_in_flight, table_log2_capacity=table_log2_capacity)
-        op.reserved[0] = 1 if debug else 0
+        op = Options(frames_in_flight=frames_in_flight, table_log2_capacity=table_log2_capacity, stream=stream or None,
+                     debug=1 if debug else 0)
         ctx = C.c_void_p()
         rc = L.vx_create(device, C.byref(gd), C.byref(fd), C.byref(op), C.byref(ctx))
         if rc != VX_OK:
@@ -484,6 +487,17 @@ def synth_scan(params: SynthParams, t: int, out_xyzr=None, out_labels=None):
     labels = out_labels if out_labels is not None else np.empty(cap, np.uint32)
     n = synth_lib().vxs_scan(C.byref(params), t, _p(xyzr), _p(labels), cap)
     return xyzr[:n], labels[:n]
+
+
+def synth_generate_many(params: SynthParams, t0: int, n: int, xyzr_ptr: int, labels_ptr: int, stride_points: int, threads: int = 0):
+    """Scans t0 .. t0+n-1 into caller memory (scan s at point offset s*stride_points); returns counts [n]."""
+    if threads <= 0:
+        threads = min(64, os.cpu_count() or 1)
+    counts = np.zeros(n, np.uint32)
+    rc = synth_lib().vxs_generate_many(C.byref(params), t0, n, xyzr_ptr, labels_ptr, stride_points, _p(counts), threads)
+    if rc != 0:
+        raise VxError("vxs_generate_many failed")
+    return counts
 
 
 def synth_velo_poses(params: SynthParams, n: int):

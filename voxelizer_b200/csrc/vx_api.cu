@@ -39,6 +39,7 @@ constexpr size_t kCounterWords = 8;
 struct vx_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = false;
   VxGridGeom geom{};
   uint64_t nvox = 0;
   uint32_t words = 0;
@@ -386,7 +387,12 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
 
   c->device = device;
   VX_CREATE_CUDA(cudaSetDevice(device));
-  VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (options && options->stream) {
+    c->stream = static_cast<cudaStream_t>(options->stream);
+  } else {
+    VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
   for (int i = 0; i < EV_COUNT; ++i) VX_CREATE_CUDA(cudaEventCreate(&c->ev[i]));
   VX_CREATE_CUDA(vx_visibility_prepare());
 
@@ -428,7 +434,7 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
 
   if (options) {
     if (options->table_log2_capacity) c->log2_target = options->table_log2_capacity;
-    c->keep_tables = (options->reserved[0] & 1u) != 0;
+    c->keep_tables = (options->debug & 1u) != 0;
   }
   if (c->log2_target < 10) c->log2_target = 10;
   if (c->log2_target > 30) c->log2_target = 30;
@@ -467,7 +473,7 @@ void vx_destroy(vx_ctx* c) {
   if (c->d_stage) cudaFree(c->d_stage);
   for (int i = 0; i < EV_COUNT; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -577,7 +583,7 @@ int vx_debug_dump(vx_ctx* c, uint32_t frame_index, int kind, void* dst, uint64_t
   VX_CUDA(c, cudaSetDevice(c->device));
   const VxSlot& s = c->slots[frame_index].dev;
   if (kind == VX_DUMP_HIST_TARGET || kind == VX_DUMP_HIST_INPUT) {
-    if (!c->keep_tables || !c->tables_dirty) return fail(c, VX_ERR_INVALID, "histogram dump needs vx_options.reserved[0] = 1");
+    if (!c->keep_tables || !c->tables_dirty) return fail(c, VX_ERR_INVALID, "histogram dump needs vx_options.debug = 1");
     const VxTable& t = kind == VX_DUMP_HIST_TARGET ? s.target : s.input;
     uint32_t used = 0;
     VX_CUDA(c, cudaMemcpy(&used, t.used_count, 4, cudaMemcpyDeviceToHost));

@@ -320,6 +320,24 @@ void vxs_velo_pose(const vxs_params* p, uint32_t t, double* V16) { velo_pose(*p,
 // Tr (velodyne -> camera), row-major 3x4.
 void vxs_calib_tr(double* tr12) { std::memcpy(tr12, kTr, sizeof(kTr)); }
 
+// Generates scans t0 .. t0+n-1 straight into caller memory (e.g. pinned host buffers): scan s goes to
+// xyzr + 4*s*stride_points and labels + s*stride_points; counts[s] receives its number of returns.
+int vxs_generate_many(const vxs_params* p, uint32_t t0, uint32_t n, float* xyzr, uint32_t* labels, uint64_t stride_points,
+                      uint32_t* counts, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  const uint32_t cap = uint32_t(stride_points < (uint64_t)p->n_beams * p->n_azimuth ? stride_points : (uint64_t)p->n_beams * p->n_azimuth);
+  auto work = [&](int tid) {
+    for (uint32_t s = uint32_t(tid); s < n; s += uint32_t(n_threads)) {
+      const uint32_t got = scan_impl(*p, t0 + s, xyzr + 4 * size_t(s) * stride_points, labels + size_t(s) * stride_points, cap);
+      counts[s] = got < cap ? got : cap;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < n_threads; ++i) th.emplace_back(work, i);
+  for (auto& x : th) x.join();
+  return 0;
+}
+
 // Writes a KITTI-format sequence directory.  Returns 0 on success.
 int vxs_write_sequence(const vxs_params* p, const char* dir, uint32_t n_scans, int write_labels, int n_threads) {
   const std::string base(dir);
