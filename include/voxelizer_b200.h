@@ -118,6 +118,12 @@ typedef struct vx_stage_times {
   uint64_t pack_launches;
   uint64_t rays_cast; /* occludedBy calls (all passes) */
   uint64_t dda_steps; /* cells traversed by those rays */
+  /* K4 anatomy, summed over frames: waves run, waves that needed the in-wave fix-point, fix-point
+   * rounds, and SM cycles spent per phase (snapshot, resolve, trace, apply) as seen by one thread. */
+  uint64_t vis_waves;
+  uint64_t vis_resolve_waves;
+  uint64_t vis_rounds;
+  uint64_t vis_cycles[4];
 } vx_stage_times;
 
 const char* vx_last_global_error(void); /* for failures before a context exists */

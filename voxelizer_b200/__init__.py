@@ -74,10 +74,11 @@ class StageTimes(C.Structure):
         ("pack_ms", C.c_double), ("total_ms", C.c_double), ("frames", C.c_uint64), ("points_read", C.c_uint64),
         ("fill_launches", C.c_uint64), ("vote_launches", C.c_uint64), ("emit_launches", C.c_uint64),
         ("visibility_launches", C.c_uint64), ("pack_launches", C.c_uint64), ("rays_cast", C.c_uint64), ("dda_steps", C.c_uint64),
+        ("vis_waves", C.c_uint64), ("vis_resolve_waves", C.c_uint64), ("vis_rounds", C.c_uint64), ("vis_cycles", C.c_uint64 * 4),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "vis_cycles" else getattr(self, n)) for n, _ in self._fields_}
 
 
 class ConfigPod(C.Structure):

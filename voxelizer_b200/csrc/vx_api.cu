@@ -32,7 +32,7 @@ struct SlotMem {
 enum { EV_BEGIN = 0, EV_FILL, EV_VOTE, EV_EMIT, EV_VIS, EV_PACK, EV_END, EV_COUNT };
 
 // per-slot counter block (uint32 words): used/overflow of both tables, then two 64-bit statistics
-constexpr size_t kCounterWords = 8;
+constexpr size_t kCounterWords = 4 + 2 * VX_SLOT_STATS + 2;  // 24 words = 96 bytes per slot
 
 }  // namespace
 
@@ -42,6 +42,7 @@ struct vx_ctx {
   bool own_stream = false;
   VxGridGeom geom{};
   uint64_t nvox = 0;
+  uint64_t visits = 0;  // cell visits per visibility pass
   uint32_t words = 0;
   float min_extent[3]{}, max_extent[3]{};
 
@@ -116,7 +117,7 @@ size_t table_bytes(uint32_t log2_cap) {
 size_t slot_bytes(const vx_ctx* c) {
   const size_t nv = c->nvox, w = c->words;
   return table_bytes(c->log2_target) + table_bytes(c->log2_input) + 2 * align_up(nv * 8, 256) + 3 * align_up((size_t)w * 4, 256) +
-         align_up(nv * 4, 256) + align_up(nv * 2, 256) + 3 * align_up((size_t)w * 4, 256);
+         align_up(nv * 4, 256) + align_up(nv * 2, 256) + 3 * align_up((size_t)w * 4, 256) + align_up(c->visits, 256);
 }
 
 int alloc_slot(vx_ctx* c, uint32_t index) {
@@ -148,6 +149,7 @@ int alloc_slot(vx_ctx* c, uint32_t index) {
   s.dev.occl = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
   s.dev.alive = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
   s.dev.memo = reinterpret_cast<uint32_t*>(take(c->nvox * 4));
+  s.dev.rayhit = reinterpret_cast<uint8_t*>(take(c->visits));
   s.dev.out_label = reinterpret_cast<uint16_t*>(take(c->nvox * 2));
   s.dev.out_bin = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
   s.dev.out_occluded = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
@@ -304,14 +306,13 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   c->last_batch = nb;
 
   bool overflow = false;
-  uint64_t rays = 0, steps = 0;
+  unsigned long long stats[VX_SLOT_STATS] = {0};
   for (uint32_t f = 0; f < nb; ++f) {
     const uint32_t* w = c->h_counters + (size_t)f * kCounterWords;
     if (w[1] || w[3]) overflow = true;
-    unsigned long long rs[2];
+    unsigned long long rs[VX_SLOT_STATS];
     std::memcpy(rs, w + 4, sizeof(rs));
-    rays += rs[0];
-    steps += rs[1];
+    for (int k = 0; k < VX_SLOT_STATS; ++k) stats[k] += rs[k];
   }
   if (overflow) return VX_ERR_TABLE_OVERFLOW;
 
@@ -333,8 +334,12 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   c->times.emit_launches += 1;
   c->times.visibility_launches += 1;
   c->times.pack_launches += 1;
-  c->times.rays_cast += rays;
-  c->times.dda_steps += steps;
+  c->times.rays_cast += stats[0];
+  c->times.dda_steps += stats[1];
+  c->times.vis_waves += stats[2];
+  c->times.vis_resolve_waves += stats[3];
+  c->times.vis_rounds += stats[4];
+  for (int k = 0; k < 4; ++k) c->times.vis_cycles[k] += stats[5 + k];
   return VX_OK;
 }
 
@@ -409,6 +414,7 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
     return bail(VX_ERR_UNSUPPORTED);
   }
   c->words = (uint32_t)((c->nvox + 31) / 32);
+  c->visits = vx_visibility_visits(c->geom);
 
   // label filter LUT (voxelize_utils.cpp:175-180,195-198): label -> joined label -> in `ignore`?
   c->filter.min_range = filter->min_range;

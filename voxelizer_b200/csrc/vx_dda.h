@@ -100,44 +100,48 @@ VX_HD int32_t vx_step_axis(float t0, float t1, float t2) {
 //              if (occupied) { hit; break; }  /* record the cell */
 //              if (!r.advance()) break; }
 // advance() returns false when the reference loop would `break` after the step (VoxelGrid.cpp:307-308).
+// Kept in scalars and stepped without branches: a ray step is the unit of work of the whole path.
 struct VxRay {
   int32_t i, j, k;
-  VxAxis ax, ay, az;
+  float tx, ty, tz;     // NextCrossingT
+  float dx, dy, dz;     // DeltaT
+  int32_t sx, sy, sz;   // Step
+  int32_t ox, oy, oz;   // Out
+  int32_t ex, ey, ez;   // end voxel
 
   VX_HD void begin(const VxGridGeom& g, int32_t si, int32_t sj, int32_t sk, float e0, float e1, float e2) {
     i = si;
     j = sj;
     k = sk;
-    ax = vx_axis_setup(g.off[0], g.res, g.nx, si, e0);
-    ay = vx_axis_setup(g.off[1], g.res, g.ny, sj, e1);
-    az = vx_axis_setup(g.off[2], g.res, g.nz, sk, e2);
+    const VxAxis ax = vx_axis_setup(g.off[0], g.res, g.nx, si, e0);
+    const VxAxis ay = vx_axis_setup(g.off[1], g.res, g.ny, sj, e1);
+    const VxAxis az = vx_axis_setup(g.off[2], g.res, g.nz, sk, e2);
+    tx = ax.tmax; dx = ax.tdelta; sx = ax.step; ox = ax.out; ex = ax.end;
+    ty = ay.tmax; dy = ay.tdelta; sy = ay.step; oy = ay.out; ey = ay.end;
+    tz = az.tmax; dz = az.tdelta; sz = az.step; oz = az.out; ez = az.end;
   }
 
   VX_HD bool inside(const VxGridGeom& g) const {
-    return i >= 0 && j >= 0 && k >= 0 && i < g.nx && j < g.ny && k < g.nz;
+    return (uint32_t)i < (uint32_t)g.nx && (uint32_t)j < (uint32_t)g.ny && (uint32_t)k < (uint32_t)g.nz;
   }
 
   // axis the NEXT advance() will move along
-  VX_HD int32_t next_axis() const { return vx_step_axis(ax.tmax, ay.tmax, az.tmax); }
+  VX_HD int32_t next_axis() const { return vx_step_axis(tx, ty, tz); }
 
   VX_HD bool advance() {
     const int32_t a = next_axis();
-    bool left;
-    if (a == 0) {
-      i += ax.step;
-      ax.tmax = VX_FADD(ax.tmax, ax.tdelta);
-      left = (i == ax.out);
-    } else if (a == 1) {
-      j += ay.step;
-      ay.tmax = VX_FADD(ay.tmax, ay.tdelta);
-      left = (j == ay.out);
-    } else {
-      k += az.step;
-      az.tmax = VX_FADD(az.tmax, az.tdelta);
-      left = (k == az.out);
-    }
-    if (left) return false;
-    if (i == ax.end && j == ay.end && k == az.end) return false;
+    const bool a0 = a == 0, a1 = a == 1, a2 = a == 2;
+    const float nx_ = VX_FADD(tx, dx), ny_ = VX_FADD(ty, dy), nz_ = VX_FADD(tz, dz);
+    i += a0 ? sx : 0;
+    j += a1 ? sy : 0;
+    k += a2 ? sz : 0;
+    tx = a0 ? nx_ : tx;
+    ty = a1 ? ny_ : ty;
+    tz = a2 ? nz_ : tz;
+    const int32_t pos = a0 ? i : (a1 ? j : k);
+    const int32_t out = a0 ? ox : (a1 ? oy : oz);
+    if (pos == out) return false;
+    if (i == ex && j == ey && k == ez) return false;
     return true;
   }
 };

@@ -15,6 +15,7 @@
 
 #define VX_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define VX_MAX_PROBES 4096u
+#define VX_SLOT_STATS 9
 
 // Open-addressing histogram of one grid of one frame: (L << 16 | label16) -> count.
 struct VxTable {
@@ -35,12 +36,13 @@ struct VxSlot {
   uint32_t* occ;              // [words] target grid occupancy (count > 0), bit L
   uint32_t* occl;             // [words] occlusions_ > -1
   uint32_t* alive;            // [words] invalid_ != -1
-  uint32_t* memo;             // [nvox]  occludedBy_ as (epoch << 26 | tau << 1 | hit)
+  uint32_t* memo;             // [nvox]  occludedBy_ as (epoch << 25 | tau of the latest ray), 0xFFFFFFFF = dead
+  uint8_t* rayhit;            // [visits] result of the ray cast at visit tau of the current pass
   uint16_t* out_label;        // [nvox]
   uint32_t* out_bin;          // [words] MSB-first packed
   uint32_t* out_occluded;     // [words]
   uint32_t* out_invalid;      // [words]
-  unsigned long long* counters;  // [2] rays, steps (statistics)
+  unsigned long long* counters;  // [VX_SLOT_STATS] rays, steps, waves, resolve waves, rounds, cycles[4]
 };
 
 // One (frame, scan) unit of fill work.
