@@ -1,24 +1,33 @@
 // TEST INFRASTRUCTURE: sequential CPU model of the wave-parallel visibility algorithm that
 // voxelizer_b200/csrc/vx_visibility.cu runs on the GPU ("K4").  It shares the product's
-// ray arithmetic header (vx_dda.h) and executes the kernel's phases in an ORDER-SCRAMBLED way (casters
-// are traced in a pseudo-random order, merges are max-reductions) so that a test passing here shows
-// the formulation is independent of thread scheduling.  tests/test_wave_model.py checks it bit for
-// bit against the oracle (reference VoxelGrid::updateOcclusions / updateInvalid, VoxelGrid.cpp:98-316).
+// ray arithmetic header (vx_dda.h) and executes the kernel's phases in an ORDER-SCRAMBLED way (work
+// lists are processed in pseudo-random order, merges are max-reductions, the resolve loop sees its
+// own updates immediately) so that a test passing here shows the formulation is independent of
+// thread scheduling.  tests/test_wave_model.py checks it bit for bit against the oracle (reference
+// VoxelGrid::updateOcclusions / updateInvalid, VoxelGrid.cpp:98-316).
 //
 // The algorithm, per pass (one endpoint) -- identical to the kernel:
-//   cells are visited in the reference order; visit number tau.  A WAVE is a tau-contiguous run of
-//   whole columns of one face of one shell (at most W cells).  Waves are processed in order:
-//   A. snapshot: for each cell of the wave read the memo (latest ray that crossed it so far in this
-//      pass).  skip = invalid pass and cell no longer alive.  candidate = not skip and memo unset.
-//   B. resolve which candidates really cast: c casts iff no CASTING candidate with smaller tau covers
-//      c with the part of its ray that lies inside this wave (rays are monotone per axis, so a ray
-//      never re-enters the face).  Solved as a monotone fix-point over undecided candidates.
-//   C. every caster traces its ray; each traversed cell t gets memo[t] = max(memo[t], (tau,hit));
-//      cells of the same wave with tau_t >= tau_caster also merge into the snapshot.
-//   D. apply the visit rule from the snapshot: occlusion pass  occluded[c] = hit (last visit wins);
-//      invalid pass  alive[c] &= hit.
+//   cells are visited in the reference order (shell / face / column / z).  A cell is LIVE when the
+//   visit can change anything: free (occupied cells answer with their own index without a ray and
+//   are never crossed by one) and, in an invalid pass, not yet killed.  A WAVE is a run of whole
+//   columns of one face holding at most `max_live` live cells.  Waves are processed in order:
+//   A. snapshot: owner[r] = id of the latest ray that crossed live cell r so far in this pass
+//      (memo, epoch-tagged); cells nothing crossed yet are CANDIDATES.
+//   B. resolve which candidates really cast: c casts iff no CASTING candidate with smaller rank
+//      crosses c with the part of its ray that lies inside this wave's face (rays are monotone per
+//      axis, so a ray never re-enters the face).  Counter formulation: cnt[c] = number of UNDECIDED
+//      earlier candidates crossing c.  killed[c] -> does not cast; cnt[c] == 0 -> casts (kills its
+//      successors); a candidate that turns out not to cast releases (decrements) its successors.
+//      Candidates whose first step is certainly along the face normal have no successors and skip the walk.
+//   C. casters get ray ids in visit order (id_base + rank among the wave's casters) and trace:
+//      memo[cell] = max(memo[cell], id); wave cells at or after the caster also merge into owner[];
+//      hit[id] = the ray ended on an occupied cell.
+//   D. apply the visit rule: occlusion pass  occluded[c] = hit[owner] (last visit wins); invalid
+//      pass  hit[owner] == 0 kills the cell.
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -29,10 +38,12 @@ namespace {
 struct Model {
   VxGridGeom g;
   size_t nvox;
-  std::vector<uint32_t> occ, alive, occl;  // bitmaps over L = (i*ny + j)*nz + k
-  std::vector<uint32_t> memo;              // (epoch << 26) | (tau << 1) | hit
+  std::vector<uint32_t> occ, live, occl;  // bitmaps over L = (i*ny + j)*nz + k
+  std::vector<uint32_t> memo;              // (epoch << 25) | ray id
+  std::vector<uint8_t> hit;                // per ray id of the current pass
   uint32_t epoch = 0;
-  uint32_t wave_cells = 8192;
+  uint32_t max_live = 2048;
+  uint32_t max_cols = 512;
   uint64_t rng = 1;
   // stats
   uint64_t n_rays = 0, n_steps = 0, n_waves = 0, n_resolve_waves = 0, n_rounds = 0, max_rounds = 0, n_prefix_steps = 0, n_unset = 0;
@@ -48,197 +59,208 @@ struct Model {
     rng = rng * 6364136223846793005ull + 1442695040888963407ull;
     return uint32_t(rng >> 33);
   }
+  template <class T>
+  void shuffle(std::vector<T>& v) {
+    for (size_t a = v.size(); a > 1; --a) std::swap(v[a - 1], v[next_rand() % a]);
+  }
 
   struct Wave {
-    int face, o;
+    int face;                // 0: i fixed, outer j; 1/2: j fixed, outer i
+    int32_t fixed;           // the fixed coordinate
     int32_t a_begin, a_end;  // outer coordinate range
-    uint32_t tau_base;
-    int32_t fixed;  // i for face 0, j for faces 1/2
   };
 
-  void cell_of(const Wave& w, uint32_t q, int32_t& i, int32_t& j, int32_t& k) const {
-    const int32_t col = int32_t(q / uint32_t(g.nz));
-    k = int32_t(q % uint32_t(g.nz));
-    if (w.face == 0) {
-      i = w.fixed;
-      j = w.a_begin + col;
-    } else {
-      i = w.a_begin + col;
-      j = w.fixed;
-    }
-  }
-  // local index of (i,j,k) inside wave w, or -1
-  int32_t local_of(const Wave& w, int32_t i, int32_t j, int32_t k) const {
-    if (w.face == 0) {
-      if (i != w.fixed || j < w.a_begin || j >= w.a_end) return -1;
-      return (j - w.a_begin) * g.nz + k;
-    }
-    if (j != w.fixed || i < w.a_begin || i >= w.a_end) return -1;
-    return (i - w.a_begin) * g.nz + k;
+  // wave-local column of (i,j), or -1
+  int32_t col_of(const Wave& w, int32_t i, int32_t j) const {
+    const int32_t fx = w.face == 0 ? i : j, outer = w.face == 0 ? j : i;
+    if (fx != w.fixed || outer < w.a_begin || outer >= w.a_end) return -1;
+    return outer - w.a_begin;
   }
 
-  // in-wave cells (tau larger than the caster's) crossed by candidate c's ray before it leaves the
-  // face, hits, or terminates
-  template <class F>
-  void prefix_walk(const Wave& w, uint32_t qc, const float* e, F f) {
+  struct LiveCell {
     int32_t i, j, k;
-    cell_of(w, qc, i, j, k);
-    if (bit(occ, lin(i, j, k))) return;  // occupied start: nothing traversed
-    VxRay r;
-    r.begin(g, i, j, k, e[0], e[1], e[2]);
-    for (;;) {
-      const int32_t a = r.next_axis();
-      const bool leaves_face = (w.face == 0) ? (a == 0) : (a == 1);
-      if (leaves_face) return;
-      if (!r.advance()) return;
-      if (!r.inside(g)) return;
-      ++n_prefix_steps;
-      if (bit(occ, lin(r.i, r.j, r.k))) return;
-      const int32_t q = local_of(w, r.i, r.j, r.k);
-      if (q > int32_t(qc)) f(uint32_t(q));
-    }
+  };
+
+  // true when the first step of the ray from (i,j,k) towards e is certainly along `normal`
+  bool normal_first(int32_t i, int32_t j, int32_t k, const float* e, int normal) const {
+    const float d[3] = {std::fabs(e[0] - vx_voxel_centre(g.off[0], g.res, i)), std::fabs(e[1] - vx_voxel_centre(g.off[1], g.res, j)),
+                        std::fabs(e[2] - vx_voxel_centre(g.off[2], g.res, k))};
+    const float other = std::max(d[(normal + 1) % 3], d[(normal + 2) % 3]);
+    return d[normal] > 1.0001f * other;
   }
 
-  void run_wave(const Wave& w, const float* e, bool inv) {
-    const uint32_t n = uint32_t(w.a_end - w.a_begin) * uint32_t(g.nz);
-    std::vector<uint32_t> snap(n, 0);  // 0 unset; (rank << 1) | hit, rank 1 = earlier waves, q+2 = in-wave caster q
-    std::vector<uint8_t> skip(n, 0);
-    std::vector<uint32_t> cand;
-    // ---- A
-    for (uint32_t q = 0; q < n; ++q) {
-      int32_t i, j, k;
-      cell_of(w, q, i, j, k);
-      const size_t L = lin(i, j, k);
-      if (inv && !bit(alive, L)) {
-        skip[q] = 1;
-        continue;
+  void run_wave(const Wave& w, const float* e, bool inv, uint32_t& id_base) {
+    const int normal = w.face == 0 ? 0 : 1;
+    // ---- A: live cells in visit order, rank lookup, snapshot
+    std::vector<LiveCell> cells;
+    std::vector<int32_t> rank_of(size_t(w.a_end - w.a_begin) * size_t(g.nz), -1);
+    for (int32_t a = w.a_begin; a < w.a_end; ++a)
+      for (int32_t k = 0; k < g.nz; ++k) {
+        const int32_t i = w.face == 0 ? w.fixed : a, j = w.face == 0 ? a : w.fixed;
+        if (bit(live, lin(i, j, k))) {
+          rank_of[size_t(a - w.a_begin) * size_t(g.nz) + size_t(k)] = int32_t(cells.size());
+          cells.push_back({i, j, k});
+        }
       }
-      const uint32_t m = memo[L];
-      if ((m >> 26) == epoch) snap[q] = 2u | (m & 1u);
-      else cand.push_back(q);
-    }
+    const uint32_t n = uint32_t(cells.size());
     ++n_waves;
-    // ---- B (monotone fix-point; status 0 undecided, 1 cast, 2 not)
-    std::vector<uint8_t> status(n, 0);
+    const uint32_t SET = 0x80000000u;
+    std::vector<uint32_t> owner(n, 0);  // 0 = candidate; SET | id otherwise.  Doubles as cnt[] during B.
+    std::vector<uint32_t> cand;
+    for (uint32_t r = 0; r < n; ++r) {
+      const uint32_t m = memo[lin(cells[r].i, cells[r].j, cells[r].k)];
+      if ((m >> 25) == epoch) owner[r] = SET | (m & 0x1FFFFFFu);
+      else cand.push_back(r);
+    }
+    auto live_rank = [&](int32_t i, int32_t j, int32_t k) -> int32_t {
+      const int32_t c = col_of(w, i, j);
+      return c < 0 ? -1 : rank_of[size_t(c) * size_t(g.nz) + size_t(k)];
+    };
+    // in-face part of candidate rc's ray: calls f(rank) for live wave cells with larger rank
+    auto prefix_walk = [&](uint32_t rc, auto f) {
+      VxRay r;
+      r.begin(g, cells[rc].i, cells[rc].j, cells[rc].k, e[0], e[1], e[2]);
+      for (;;) {
+        if (r.next_axis() == normal) return;
+        if (!r.advance()) return;
+        if (!r.inside(g)) return;
+        ++n_prefix_steps;
+        if (bit(occ, lin(r.i, r.j, r.k))) return;
+        const int32_t x = live_rank(r.i, r.j, r.k);
+        if (x > int32_t(rc)) f(uint32_t(x));
+      }
+    };
+    // ---- B: counters
     std::vector<uint32_t> casters;
-    {
-      bool any_forward = false;
-      for (uint32_t qc : cand) prefix_walk(w, qc, e, [&](uint32_t) { any_forward = true; });
-      if (!any_forward) {
-        casters = cand;
-      } else {
-        ++n_resolve_waves;
-        const uint32_t INF = 0xFFFFFFFFu;
-        std::vector<uint32_t> cov_cast(n, INF);
-        std::vector<uint32_t> undecided = cand;
-        uint64_t rounds = 0;
-        while (!undecided.empty()) {
-          ++rounds;
-          std::vector<uint32_t> cov_und(n, INF);
-          for (uint32_t qc : undecided) prefix_walk(w, qc, e, [&](uint32_t q) { cov_und[q] = std::min(cov_und[q], qc); });
-          std::vector<uint32_t> next;
-          std::vector<uint32_t> newly;
-          for (uint32_t qc : undecided) {
-            if (cov_cast[qc] < qc) status[qc] = 2;
-            else if (cov_und[qc] >= qc) {
-              status[qc] = 1;
-              newly.push_back(qc);
-            } else next.push_back(qc);
+    if (!cand.empty()) {
+      std::vector<uint8_t> status(n, 0), killed(n, 0), has_succ(n, 0);  // status: 0 undecided, 1 cast, 2 not
+      bool any = false;
+      std::vector<uint32_t> order = cand;
+      shuffle(order);
+      for (uint32_t rc : order) {
+        if (normal_first(cells[rc].i, cells[rc].j, cells[rc].k, e, normal)) continue;
+        prefix_walk(rc, [&](uint32_t x) {
+          if (!(owner[x] & SET)) {
+            owner[x] += 1;
+            has_succ[rc] = 1;
+            any = true;
           }
-          for (uint32_t qc : newly) prefix_walk(w, qc, e, [&](uint32_t q) { cov_cast[q] = std::min(cov_cast[q], qc); });
-          undecided.swap(next);
+        });
+      }
+      if (any) {
+        ++n_resolve_waves;
+        uint64_t rounds = 0;
+        size_t undecided = cand.size();
+        while (undecided) {
+          ++rounds;
+          shuffle(order);
+          for (uint32_t rc : order) {
+            if (status[rc]) continue;
+            if (killed[rc]) {
+              status[rc] = 2;
+              --undecided;
+              if (has_succ[rc]) prefix_walk(rc, [&](uint32_t x) { if (!(owner[x] & SET)) owner[x] -= 1; });
+            } else if (owner[rc] == 0) {
+              status[rc] = 1;
+              --undecided;
+              if (has_succ[rc]) prefix_walk(rc, [&](uint32_t x) { if (!(owner[x] & SET)) killed[x] = 1; });
+            }
+          }
         }
         n_rounds += rounds;
         max_rounds = std::max(max_rounds, rounds);
-        for (uint32_t qc : cand)
-          if (status[qc] == 1) casters.push_back(qc);
+        for (uint32_t rc : cand) {
+          owner[rc] = 0;
+          if (status[rc] == 1) casters.push_back(rc);
+        }
+      } else {
+        casters = cand;
       }
     }
-    // ---- C (scrambled order)
-    for (size_t a = casters.size(); a > 1; --a) std::swap(casters[a - 1], casters[next_rand() % a]);
-    for (uint32_t qc : casters) {
-      int32_t i, j, k;
-      cell_of(w, qc, i, j, k);
-      const uint32_t tau = w.tau_base + qc;
+    // ---- C: ids in visit order, traced in scrambled order
+    std::vector<uint32_t> slot(casters.size());
+    for (uint32_t s = 0; s < slot.size(); ++s) slot[s] = s;
+    shuffle(slot);
+    if (hit.size() < size_t(id_base) + casters.size()) hit.resize(size_t(id_base) + casters.size() + 1024, 0);
+    for (uint32_t s : slot) {
+      const uint32_t rc = casters[s];
+      const uint32_t id = id_base + s;
+      const uint32_t enc = (epoch << 25) | id;
       ++n_rays;
-      bool hit = false;
-      uint32_t len = 0;
-      if (bit(occ, lin(i, j, k))) {
-        hit = true;
-      } else {
-        VxRay r;
-        r.begin(g, i, j, k, e[0], e[1], e[2]);
-        for (;;) {
-          if (!r.inside(g)) break;
-          if (bit(occ, lin(r.i, r.j, r.k))) {
-            hit = true;
-            break;
-          }
-          ++len;
-          if (!r.advance()) break;
+      VxRay r;
+      r.begin(g, cells[rc].i, cells[rc].j, cells[rc].k, e[0], e[1], e[2]);
+      bool h = false, in_face = true;
+      for (;;) {
+        if (!r.inside(g)) break;
+        const size_t L = lin(r.i, r.j, r.k);
+        if (bit(occ, L)) {
+          h = true;
+          break;
         }
-      }
-      n_steps += len;
-      const uint32_t h = hit ? 1u : 0u;
-      const uint32_t enc = (epoch << 26) | (tau << 1) | h;
-      const uint32_t senc = ((qc + 2u) << 1) | h;
-      if (len == 0) {  // occupied start: the caller's own assignment occludedBy_[idx] = idx
-        const size_t L = lin(i, j, k);
         memo[L] = std::max(memo[L], enc);
-        snap[qc] = std::max(snap[qc], senc);
-      } else {
-        VxRay r;
-        r.begin(g, i, j, k, e[0], e[1], e[2]);
-        for (uint32_t s = 0; s < len; ++s) {
-          const size_t L = lin(r.i, r.j, r.k);
-          memo[L] = std::max(memo[L], enc);
-          const int32_t q = local_of(w, r.i, r.j, r.k);
-          if (q >= int32_t(qc)) snap[size_t(q)] = std::max(snap[size_t(q)], senc);
-          if (s + 1 < len) r.advance();
+        if (in_face) {
+          const int32_t x = live_rank(r.i, r.j, r.k);
+          if (x >= int32_t(rc)) owner[size_t(x)] = std::max(owner[size_t(x)], SET | id);
         }
+        ++n_steps;
+        if (r.next_axis() == normal) in_face = false;
+        if (!r.advance()) break;
+      }
+      hit[id] = h ? 1 : 0;
+    }
+    id_base += uint32_t(casters.size());
+    // ---- D
+    for (uint32_t r = 0; r < n; ++r) {
+      const size_t L = lin(cells[r].i, cells[r].j, cells[r].k);
+      if (!(owner[r] & SET)) {
+        ++n_unset;
+        continue;
+      }
+      const bool h = hit[owner[r] & 0x1FFFFFFu] != 0;
+      if (inv) {
+        if (!h) setbit(live, L, false);
+      } else {
+        setbit(occl, L, h);
       }
     }
-    // ---- D
-    for (uint32_t q = 0; q < n; ++q) {
-      if (skip[q]) continue;
-      int32_t i, j, k;
-      cell_of(w, q, i, j, k);
-      const size_t L = lin(i, j, k);
-      if (snap[q] == 0) ++n_unset;
-      const bool hit = snap[q] & 1u;
-      if (inv) {
-        if (!hit) setbit(alive, L, false);
-      } else {
-        setbit(occl, L, hit);
+  }
+
+  // one face = a sequence of columns, cut into waves of at most max_live live cells / max_cols columns
+  void run_face(int face, int32_t fixed, int32_t outer, const float* e, bool inv, uint32_t& id_base) {
+    int32_t a = 0;
+    while (a < outer) {
+      uint32_t lv = 0;
+      int32_t b = a;
+      while (b < outer && uint32_t(b - a) < max_cols) {
+        uint32_t c = 0;
+        for (int32_t k = 0; k < g.nz; ++k) {
+          const int32_t i = face == 0 ? fixed : b, j = face == 0 ? b : fixed;
+          c += bit(live, lin(i, j, k));
+        }
+        if (b > a && lv + c > max_live) break;
+        lv += c;
+        ++b;
       }
+      Wave w{face, fixed, a, b};
+      if (lv) run_wave(w, e, inv, id_base);
+      a = b;
     }
   }
 
   void run_pass(const float* e, bool inv) {
     epoch += 1;
-    if (epoch >= 64) {
+    if (epoch >= 127) {
       std::fill(memo.begin(), memo.end(), 0u);
       epoch = 1;
     }
+    std::fill(hit.begin(), hit.end(), 0);
+    uint32_t id_base = 0;
     const int32_t shells = vx_num_shells(g.nx, g.ny);
-    const int32_t cols_per_wave = std::max<int32_t>(1, int32_t(wave_cells) / g.nz);
-    uint32_t tau = 0;
-    for (int32_t o = 0; o < shells; ++o)
-      for (int face = 0; face < 3; ++face) {
-        const int32_t outer = face == 0 ? g.ny : g.nx - o - 1;
-        const int32_t fixed = face == 0 ? g.nx - 1 - o : (face == 1 ? o : g.ny - 1 - o);
-        for (int32_t a = 0; a < outer; a += cols_per_wave) {
-          Wave w;
-          w.face = face;
-          w.o = o;
-          w.a_begin = a;
-          w.a_end = std::min(outer, a + cols_per_wave);
-          w.tau_base = tau;
-          w.fixed = fixed;
-          run_wave(w, e, inv);
-          tau += uint32_t(w.a_end - w.a_begin) * uint32_t(g.nz);
-        }
-      }
+    for (int32_t o = 0; o < shells; ++o) {
+      run_face(0, g.nx - 1 - o, g.ny, e, inv, id_base);
+      run_face(1, o, g.nx - o - 1, e, inv, id_base);
+      run_face(2, g.ny - 1 - o, g.nx - o - 1, e, inv, id_base);
+    }
   }
 };
 
@@ -247,11 +269,12 @@ struct Model {
 extern "C" {
 
 // occ_bytes: one byte per voxel (non-zero = occupied) in OUTPUT order L = (x*ny + y)*nz + z.
-// endpoints: n_endpoints x 3.  Outputs (bytes 0/1, output order): occluded = occlusions_ > -1,
-// invalid = reference isInvalid after all passes.  stats8: rays, steps, waves, waves needing
-// resolution, total rounds, max rounds, prefix steps, reserved.
+// endpoints: n_endpoints x 3.  max_live: live cells per wave (columns are never split).
+// Outputs (bytes 0/1, output order): occluded = occlusions_ > -1, invalid = reference isInvalid after
+// all passes.  stats8: rays, steps, waves, waves needing resolution, total rounds, max rounds, prefix
+// steps, live cells left without an owner (must be 0).
 void wm_run(const int32_t* size3, float res, const float* off3, const uint8_t* occ_bytes, uint32_t n_endpoints,
-            const float* endpoints, uint32_t wave_cells, uint64_t seed, uint8_t* occluded, uint8_t* invalid, uint64_t* stats8) {
+            const float* endpoints, uint32_t max_live, uint64_t seed, uint8_t* occluded, uint8_t* invalid, uint64_t* stats8) {
   Model m;
   m.g.nx = size3[0];
   m.g.ny = size3[1];
@@ -263,20 +286,24 @@ void wm_run(const int32_t* size3, float res, const float* off3, const uint8_t* o
   m.nvox = size_t(size3[0]) * size_t(size3[1]) * size_t(size3[2]);
   const size_t words = (m.nvox + 31) / 32;
   m.occ.assign(words, 0);
-  m.alive.assign(words, 0);
+  m.live.assign(words, 0);
   m.occl.assign(words, 0);
   m.memo.assign(m.nvox, 0);
-  m.wave_cells = wave_cells;
+  m.max_live = max_live < 1 ? 1 : max_live;
   m.rng = seed * 2 + 1;
   for (size_t L = 0; L < m.nvox; ++L)
     if (occ_bytes[L]) Model::setbit(m.occ, L, true);
+  // occupied cells: occludedBy returns their own index at once (VoxelGrid.cpp:246-247 via 286-296), so
+  // occlusions_ > -1 and invalid_ == own index for good; no ray ever records them.  They are not live.
+  for (size_t L = 0; L < m.nvox; ++L) Model::setbit(m.live, L, !Model::bit(m.occ, L));
+  m.occl = m.occ;
   const float origin[3] = {0, 0, 0};
   m.run_pass(origin, false);
-  m.alive = m.occl;  // invalid_ = occlusions_
+  for (size_t w = 0; w < words; ++w) m.live[w] = m.occl[w] & ~m.occ[w];  // invalid_ = occlusions_
   for (uint32_t p = 0; p < n_endpoints; ++p) m.run_pass(endpoints + 3 * size_t(p), true);
   for (size_t L = 0; L < m.nvox; ++L) {
     occluded[L] = Model::bit(m.occl, L);
-    invalid[L] = Model::bit(m.alive, L) && !Model::bit(m.occ, L);
+    invalid[L] = Model::bit(m.live, L);
   }
   if (stats8) {
     stats8[0] = m.n_rays;

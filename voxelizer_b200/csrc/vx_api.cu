@@ -117,7 +117,7 @@ size_t table_bytes(uint32_t log2_cap) {
 size_t slot_bytes(const vx_ctx* c) {
   const size_t nv = c->nvox, w = c->words;
   return table_bytes(c->log2_target) + table_bytes(c->log2_input) + 2 * align_up(nv * 8, 256) + 3 * align_up((size_t)w * 4, 256) +
-         align_up(nv * 4, 256) + align_up(nv * 2, 256) + 3 * align_up((size_t)w * 4, 256) + align_up(c->visits, 256);
+         align_up(nv * 4, 256) + align_up(nv * 2, 256) + 3 * align_up((size_t)w * 4, 256) + align_up((c->visits / 32 + 1) * 4, 256);
 }
 
 int alloc_slot(vx_ctx* c, uint32_t index) {
@@ -149,7 +149,7 @@ int alloc_slot(vx_ctx* c, uint32_t index) {
   s.dev.occl = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
   s.dev.alive = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
   s.dev.memo = reinterpret_cast<uint32_t*>(take(c->nvox * 4));
-  s.dev.rayhit = reinterpret_cast<uint8_t*>(take(c->visits));
+  s.dev.hitbits = reinterpret_cast<uint32_t*>(take((c->visits / 32 + 1) * 4));
   s.dev.out_label = reinterpret_cast<uint16_t*>(take(c->nvox * 2));
   s.dev.out_bin = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
   s.dev.out_occluded = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));

@@ -35,9 +35,9 @@ struct VxSlot {
   unsigned long long* best_target;  // [nvox]
   uint32_t* occ;              // [words] target grid occupancy (count > 0), bit L
   uint32_t* occl;             // [words] occlusions_ > -1
-  uint32_t* alive;            // [words] invalid_ != -1
-  uint32_t* memo;             // [nvox]  occludedBy_ as (epoch << 25 | tau of the latest ray), 0xFFFFFFFF = dead
-  uint8_t* rayhit;            // [visits] result of the ray cast at visit tau of the current pass
+  uint32_t* alive;            // [words] free cells with invalid_ != -1 (the traversal's live set)
+  uint32_t* memo;             // [nvox]  occludedBy_ as (pass epoch << 25 | id of the latest ray that crossed the cell)
+  uint32_t* hitbits;          // [visits / 32 + 1] ray id -> the ray ended on an occupied cell (current pass)
   uint16_t* out_label;        // [nvox]
   uint32_t* out_bin;          // [words] MSB-first packed
   uint32_t* out_occluded;     // [words]

@@ -5,65 +5,70 @@
 // The reference is order dependent: a ray writes its result into occludedBy_ for every cell it
 // crossed, unconditionally, and a cell visited later reads whatever the LATEST ray that crossed it
 // left there (casting its own ray only if nothing has crossed it yet).  Casting one independent ray
-// per voxel flips ~60 k output bits per frame.  This kernel keeps the reference's visit order as a
-// timestamp and parallelises inside it:
+// per voxel flips ~60 k output bits per frame.  This kernel keeps the reference's visit order and
+// parallelises inside it (tests/model/wave_model.cpp is the CPU model of exactly this formulation):
 //
-//   * visit number tau: position of a cell visit in the reference's shell / face / column / z order.
-//   * memo[L] = (epoch << 25) | tau_ray, merged with atomicMax: what a visit reads is the ray with the
-//     largest tau that crossed the cell = the latest writer; that ray's result (hit / miss) is looked
-//     up in rayhit[tau_ray], written once by the ray when it ends -- so a ray is walked ONCE.
-//     `epoch` = pass number, so the reference's "fill occludedBy_ with -2" costs nothing.
-//     0xFFFFFFFF = the cell is DEAD (invalid_ == -1): every later pass skips it, atomicMax keeps it dead.
-//   * a WAVE = a tau-contiguous run of whole columns of one face (<= kWaveCells cells).  One CTA owns
-//     one frame and runs its waves in order; inside a wave
-//       A  snapshot the memo of every cell; candidates = visited cells nothing has crossed yet;
-//       B  decide which candidates cast: c casts iff no CASTING candidate with smaller tau crosses c
-//          with the in-face prefix of its ray (rays are monotone per axis, so they never re-enter a
-//          face).  Monotone fix-point over the undecided candidates, all in shared memory;
-//       C  casters trace their rays in parallel (atomicMax into memo; cells of the same wave that
-//          are visited at or after the caster also merge into the snapshot);
-//       D  apply the visit rule from the snapshot: occlusions_[c] = memo (last visit wins) or
-//          invalid_[c] = min(invalid_[c], memo)  (a miss kills the cell).
-//   * only booleans are observable (isOccluded / isInvalid, VoxelGrid.cpp:65-73): occluded = hit,
-//     alive = hit at every visit of every pass.
-// tests/model/wave_model.cpp is the CPU model of exactly this formulation.
+//   * LIVE cells.  A visit matters only for a free cell that, in an invalid pass, has not been killed
+//     yet (invalid_ != -1).  Occupied cells answer occludedBy() with their own index at once, are
+//     never recorded by any ray (a ray stops in front of them), so they stay "occluded" and "not
+//     invalid" for good and are left out.  One bitmap (`alive`) holds the live set; a typical
+//     invalid pass touches < 20 % of the 2.6 M visits of the reference's sweep.
+//   * a WAVE = a run of whole columns of one face of one shell holding <= kMaxLive live cells,
+//     compacted into shared memory.  One CTA owns one frame and runs its waves in visit order:
+//       A  snapshot: owner[r] = id of the latest ray that crossed live cell r (global memo, tagged
+//          with the pass number so that "fill occludedBy_ with -2" costs nothing); cells nothing has
+//          crossed are CANDIDATES.
+//       B  which candidates cast?  c casts iff no CASTING candidate visited earlier crosses c with
+//          the in-face part of its ray (rays are monotone per axis: they never re-enter the face).
+//          Counters: cnt[c] = undecided earlier candidates crossing c.  killed -> no cast (releases
+//          its successors); cnt == 0 -> casts (kills its successors).  Monotone, so any thread
+//          interleaving gives the reference's answer; chains resolve in as many sweeps as they are long.
+//       C  casters get ray ids in visit order and trace: RED.MAX(memo[cell], id) = "latest ray wins";
+//          hit[id] is one bit set when the ray ends on an occupied cell.  Rays are pulled from a
+//          queue by the lanes of few warps and refilled as they end, so that a long ray does not
+//          idle a whole warp (most rays are ~25 cells, a few are > 200).
+//       D  apply the visit: hit[owner] decides -- occlusions_ (last visit wins) in pass 0, kill in
+//          an invalid pass (invalid_ = min(...) can only go to -1 once).
+//   * only booleans are observable (isOccluded / isInvalid, VoxelGrid.cpp:65-73).
 //
-// Latency-bound, not HBM-bound.  The occupancy a ray tests at every step is read-only for the whole
-// kernel and sparse (a few % of the voxels), so each CTA first compresses it into shared memory:
-// one bit per 4x4x2 block, a rank directory and one 32-bit fine mask per non-empty block; a lookup
-// is 1-3 shared-memory loads instead of an L2 round trip.  What stays in L2/HBM is the memo: one
-// coalesced read per visited cell and one fire-and-forget RED.MAX per ray step.
+// Latency- and issue-bound, not HBM-bound.  The occupancy test of a ray step reads a shared-memory
+// bitmap of 4x4x1-voxel blocks (5 % of the steps need the exact bit from global memory; that load is
+// issued one loop iteration before it is consumed).  Global traffic: one memo read per live visit,
+// one fire-and-forget RED per ray step, one hit-bit gather per live visit.
 #include "vx_launch.h"
 
 namespace {
 
-constexpr int kVisThreads = 256;
-constexpr int kWaveCells = 4096;
-constexpr int kCellsPerThread = kWaveCells / kVisThreads;
-constexpr uint32_t kSkip = 0xFFFFFFFFu;
-constexpr uint32_t kDead = 0xFFFFFFFFu;
+constexpr int kVisThreads = 128;
+constexpr int kVisWarps = kVisThreads / 32;
+constexpr int kMaxLive = 2048;    // live cells per wave
+constexpr int kMaxChunks = 512;   // chunk = <= 32 consecutive z of one column
+constexpr int kChunksPerThread = kMaxChunks / kVisThreads;
+constexpr int kLivePerThread = kMaxLive / kVisThreads;
+constexpr uint32_t kSet = 0x80000000u;
 constexpr uint32_t kEpochShift = 25;
-constexpr uint32_t kTauMask = (1u << kEpochShift) - 1u;
-constexpr uint32_t kMaxEpoch = 126;  // epochs 1..126: an encoded memo can never equal kDead
-
-// sparse occupancy in shared memory
-constexpr uint32_t kCoarseWordsMax = 2048;  // 65536 blocks of 4x4x2 voxels (256 x 256 x 32 grid)
-constexpr uint32_t kFineCap = 8192;         // non-empty blocks held in shared memory; the rest falls back to L2
+constexpr uint32_t kIdMask = (1u << kEpochShift) - 1u;
+constexpr uint32_t kMaxEpoch = 127;       // epochs 1..127 (0 = never written)
+constexpr uint32_t kCoarseWords = 4096;   // 131072 block bits
+constexpr uint32_t kRefillLanes = 8;      // idle lanes that trigger a refill of the tracer warp
 
 struct VisShared {
-  uint32_t snap[kWaveCells];  // 0 unset | kSkip | 2 + hit (crossed in an earlier wave) | (q + 2) << 1 (in-wave caster q)
-  uint16_t cand[kWaveCells];  // candidate list (local indices)
-  uint8_t status[kWaveCells]; // per candidate slot: 0 undecided, 1 casts, 2 does not
-  uint32_t cov_und[kWaveCells / 32];   // cell is crossed by an UNDECIDED earlier candidate
-  uint32_t cov_cast[kWaveCells / 32];  // cell is crossed by a DECIDED earlier caster
-  uint32_t hitbits[kWaveCells / 32];   // result of in-wave caster q
-  uint32_t coarse[kCoarseWordsMax];    // bit per 4x4x2 block: any voxel occupied
-  uint16_t rank[kCoarseWordsMax];      // number of set coarse bits before this word (saturating)
-  uint32_t fine[kFineCap];             // occupancy of the 32 voxels of the r-th non-empty block
-  uint32_t n_cand;
-  uint32_t any_forward;
-  uint32_t remaining;
-  uint32_t scan_carry;
+  uint32_t coarse[kCoarseWords];    // bit per (2^s x 2^s x 1) block: any voxel occupied
+  uint32_t owner[kMaxLive];         // per live cell: 0 unset | kSet + ray id; cnt[] of candidates during B
+  uint16_t rcell[kMaxLive];         // live rank -> chunk << 5 | bit
+  uint16_t cand[kMaxLive];          // live ranks of the candidates, then of the casters, in visit order
+  uint32_t chmask[kMaxChunks];      // live mask of a chunk
+  uint16_t chbase[kMaxChunks];      // live rank of its first live cell
+  uint32_t killed[kMaxLive / 32];   // per live rank: crossed by a decided caster
+  uint32_t decided[kMaxLive / 32];  // per candidate slot
+  uint32_t castbit[kMaxLive / 32];  // per candidate slot
+  uint32_t has_succ[kMaxLive / 32]; // per candidate slot: its in-face ray crosses a later candidate
+  uint32_t warp_sums[kVisWarps];
+  uint32_t scan_total;
+  uint32_t ncols_ok;
+  uint32_t any_edge;
+  uint32_t undecided;
+  uint32_t queue;
 };
 
 struct Wave {
@@ -71,7 +76,6 @@ struct Wave {
   int32_t fixed;    // the fixed coordinate
   int32_t a_begin;  // first outer coordinate
   int32_t ncols;
-  uint32_t tau_base;
 };
 
 struct Stats {
@@ -81,11 +85,13 @@ struct Stats {
 
 struct Frame {
   VxGridGeom g;
-  int32_t nz_shift;  // log2(nz) if nz is a power of two, else -1
-  int32_t cy, cz;    // coarse grid dims (y, z); 0 = sparse occupancy disabled (grid too large)
+  int32_t cpc;       // chunks per column = ceil(nz / 32)
+  int32_t cshift;    // coarse block = (1 << cshift)^2 x 1 voxels; -1: no coarse bitmap (grid too large)
+  int32_t cyb;       // coarse blocks along y
   const uint32_t* __restrict__ occ;
-  uint32_t* memo;
-  uint8_t* rayhit;  // [visits per pass] result of the ray cast at visit tau (this pass)
+  uint32_t* live;    // [words] free and (invalid pass) not killed
+  uint32_t* memo;    // [nvox] epoch << 25 | id of the latest ray of that pass
+  uint32_t* hitbits; // [visits / 32 + 1] ray id -> ended on an occupied cell (this pass)
   uint32_t* occl;
   float e0, e1, e2;
   uint32_t epoch;
@@ -96,282 +102,390 @@ __device__ __forceinline__ uint32_t lin(const VxGridGeom& g, int32_t i, int32_t 
   return ((uint32_t)i * (uint32_t)g.ny + (uint32_t)j) * (uint32_t)g.nz + (uint32_t)k;
 }
 
-// occupancy test of an in-grid cell
-__device__ __forceinline__ bool occupied(const Frame& f, const VisShared& sm, int32_t i, int32_t j, int32_t k) {
-  if (f.cz > 0) {
-    const uint32_t C = ((uint32_t)(i >> 2) * (uint32_t)f.cy + (uint32_t)(j >> 2)) * (uint32_t)f.cz + (uint32_t)(k >> 1);
-    const uint32_t word = sm.coarse[C >> 5];
-    const uint32_t bit = 1u << (C & 31u);
-    if (!(word & bit)) return false;
-    const uint32_t r = (uint32_t)sm.rank[C >> 5] + (uint32_t)__popc(word & (bit - 1u));
-    if (r < kFineCap) return (sm.fine[r] >> ((((uint32_t)i & 3u) * 4u + ((uint32_t)j & 3u)) * 2u + ((uint32_t)k & 1u))) & 1u;
-  }
-  const uint32_t L = lin(f.g, i, j, k);
-  return (__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u;
+// bits [L0, L0 + len) of a bitmap, len <= 32
+__device__ __forceinline__ uint32_t extract_bits(const uint32_t* bits, uint32_t L0, uint32_t len) {
+  const uint32_t w = L0 >> 5, s = L0 & 31u;
+  const uint32_t lo = __ldcg(bits + w);
+  const uint32_t hi = (s + len > 32u) ? __ldcg(bits + w + 1) : 0u;
+  const uint32_t v = __funnelshift_r(lo, hi, s);
+  return len >= 32u ? v : (v & ((1u << len) - 1u));
 }
 
-// Builds the sparse occupancy of this frame in shared memory (once per frame).
-__device__ void build_sparse_occupancy(const Frame& f, VisShared& sm) {
-  const uint32_t tid = threadIdx.x;
-  const int32_t cx = (f.g.nx + 3) >> 2;
-  const uint32_t n_blocks = (uint32_t)cx * (uint32_t)f.cy * (uint32_t)f.cz;
-  const uint32_t n_words = (n_blocks + 31u) >> 5;
-  auto block_mask = [&](uint32_t C) -> uint32_t {
-    const uint32_t ck = C % (uint32_t)f.cz;
-    const uint32_t cj = (C / (uint32_t)f.cz) % (uint32_t)f.cy;
-    const uint32_t ci = C / ((uint32_t)f.cz * (uint32_t)f.cy);
-    uint32_t m = 0;
-    for (uint32_t di = 0; di < 4; ++di)
-      for (uint32_t dj = 0; dj < 4; ++dj)
-        for (uint32_t dk = 0; dk < 2; ++dk) {
-          const int32_t i = (int32_t)(ci * 4 + di), j = (int32_t)(cj * 4 + dj), k = (int32_t)(ck * 2 + dk);
-          if (i < f.g.nx && j < f.g.ny && k < f.g.nz) {
-            const uint32_t L = lin(f.g, i, j, k);
-            m |= ((__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u) << ((di * 4 + dj) * 2 + dk);
-          }
-        }
-    return m;
-  };
-  // pass 1: coarse bits (one thread per coarse word: 32 consecutive blocks)
-  for (uint32_t w = tid; w < n_words; w += kVisThreads) {
-    uint32_t bits = 0;
-    for (uint32_t b = 0; b < 32; ++b) {
-      const uint32_t C = w * 32 + b;
-      if (C < n_blocks && block_mask(C)) bits |= 1u << b;
-    }
-    sm.coarse[w] = bits;
+// exclusive prefix sum of one value per thread over the CTA; total in sm.scan_total (valid after return)
+__device__ __forceinline__ uint32_t block_scan(VisShared& sm, uint32_t v) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, off);
+    if (lane >= (uint32_t)off) x += y;
   }
-  if (tid == 0) sm.scan_carry = 0;
+  __syncthreads();  // previous users of warp_sums / scan_total are done
+  if (lane == 31u) sm.warp_sums[warp] = x;
   __syncthreads();
-  // pass 2: exclusive prefix sum of popcounts over the coarse words (chunks of kVisThreads words)
-  for (uint32_t w0 = 0; w0 < n_words; w0 += kVisThreads) {
-    const uint32_t w = w0 + tid;
-    const uint32_t c = w < n_words ? (uint32_t)__popc(sm.coarse[w]) : 0u;
-    // block-wide inclusive scan via warp shuffles + the cand[] scratch for warp totals
-    uint32_t x = c;
-    for (int off = 1; off < 32; off <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, off);
-      if ((tid & 31u) >= (uint32_t)off) x += y;
-    }
-    uint32_t* warp_tot = sm.cov_und;  // scratch (kVisThreads / 32 entries)
-    if ((tid & 31u) == 31u) warp_tot[tid >> 5] = x;
-    __syncthreads();
-    uint32_t before = sm.scan_carry;
-    for (uint32_t ww = 0; ww < (tid >> 5); ++ww) before += warp_tot[ww];
-    const uint32_t excl = before + x - c;
-    if (w < n_words) sm.rank[w] = (uint16_t)(excl < 0xFFFFu ? excl : 0xFFFFu);
-    __syncthreads();
-    if (tid == kVisThreads - 1) sm.scan_carry = before + x;
-    __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kVisWarps; ++w) {
+    const uint32_t s = sm.warp_sums[w];
+    if ((uint32_t)w < warp) before += s;
+    total += s;
   }
-  // pass 3: fine masks of the non-empty blocks that fit
-  for (uint32_t w = tid; w < n_words; w += kVisThreads) {
-    uint32_t bits = sm.coarse[w];
-    uint32_t r = sm.rank[w];
-    while (bits) {
-      const uint32_t b = (uint32_t)__ffs(bits) - 1u;
-      bits &= bits - 1u;
-      if (r < kFineCap) sm.fine[r] = block_mask(w * 32 + b);
-      ++r;
-    }
-  }
-  __syncthreads();
+  if (threadIdx.x == 0) sm.scan_total = total;
+  return before + x - v;
 }
 
-__device__ __forceinline__ void cell_of(const Frame& f, const Wave& w, uint32_t q, int32_t& i, int32_t& j, int32_t& k) {
-  uint32_t col;
-  if (f.nz_shift >= 0) {
-    col = q >> f.nz_shift;
-    k = (int32_t)(q & ((1u << f.nz_shift) - 1u));
+__device__ __forceinline__ void wave_cell(const Frame& f, const Wave& w, uint32_t rc, int32_t& i, int32_t& j, int32_t& k) {
+  const uint32_t c = rc >> 5, bit = rc & 31u;
+  uint32_t col, part;
+  if (f.cpc == 1) {
+    col = c;
+    part = 0;
   } else {
-    col = q / (uint32_t)f.g.nz;
-    k = (int32_t)(q - col * (uint32_t)f.g.nz);
+    col = c / (uint32_t)f.cpc;
+    part = c - col * (uint32_t)f.cpc;
   }
+  k = (int32_t)(part * 32u + bit);
+  const int32_t outer = w.a_begin + (int32_t)col;
   if (w.face == 0) {
     i = w.fixed;
-    j = w.a_begin + (int32_t)col;
+    j = outer;
   } else {
-    i = w.a_begin + (int32_t)col;
+    i = outer;
     j = w.fixed;
   }
 }
 
-// local index of (i,j,k) inside the wave, or -1
-__device__ __forceinline__ int32_t local_of(const Frame& f, const Wave& w, int32_t i, int32_t j, int32_t k) {
+// live rank of (i,j,k) inside the wave, or -1
+__device__ __forceinline__ int32_t live_rank(const Frame& f, const Wave& w, const VisShared& sm, int32_t i, int32_t j, int32_t k) {
   const int32_t fx = w.face == 0 ? i : j;
-  const int32_t outer = (w.face == 0 ? j : i) - w.a_begin;
-  if (fx != w.fixed || outer < 0 || outer >= w.ncols) return -1;
-  return outer * f.g.nz + k;
+  const int32_t col = (w.face == 0 ? j : i) - w.a_begin;
+  if (fx != w.fixed || (uint32_t)col >= (uint32_t)w.ncols) return -1;
+  const uint32_t c = (uint32_t)col * (uint32_t)f.cpc + ((uint32_t)k >> 5);
+  const uint32_t bit = (uint32_t)k & 31u;
+  const uint32_t m = sm.chmask[c];
+  if (!((m >> bit) & 1u)) return -1;
+  return (int32_t)((uint32_t)sm.chbase[c] + (uint32_t)__popc(m & ((1u << bit) - 1u)));
 }
 
-// Cells of this wave, visited after candidate qc, that qc's ray would cross before it leaves the
-// face, hits an occupied cell or terminates: sets their bit in `target`.  Only LATER cells are ever
-// marked, so "bit set" means "crossed by an earlier candidate".  Returns #cells marked.
-__device__ uint32_t prefix_mark(const Frame& f, const Wave& w, const VisShared& sm, uint32_t qc, uint32_t* target) {
+__device__ __forceinline__ bool coarse_set(const Frame& f, const VisShared& sm, int32_t i, int32_t j, int32_t k) {
+  if (f.cshift < 0) return true;
+  const uint32_t C = ((uint32_t)(i >> f.cshift) * (uint32_t)f.cyb + (uint32_t)(j >> f.cshift)) * (uint32_t)f.g.nz + (uint32_t)k;
+  return (sm.coarse[C >> 5] >> (C & 31u)) & 1u;
+}
+
+__device__ __forceinline__ bool occupied_exact(const Frame& f, int32_t i, int32_t j, int32_t k) {
+  const uint32_t L = lin(f.g, i, j, k);
+  return (__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u;
+}
+
+__device__ __forceinline__ bool occupied(const Frame& f, const VisShared& sm, int32_t i, int32_t j, int32_t k) {
+  return coarse_set(f, sm, i, j, k) && occupied_exact(f, i, j, k);
+}
+
+// The first step of the ray from (i,j,k) is certainly along `normal`: its in-face part is empty.
+// (NextCrossingT = half / |dir|, VoxelGrid.cpp:257,264: the largest |dir| steps first; the 1e-4 margin
+// is far above the rounding of the division and of the conversion to float.)
+__device__ __forceinline__ bool normal_first(const Frame& f, int32_t i, int32_t j, int32_t k, int32_t normal) {
+  const float d0 = fabsf(VX_FSUB(f.e0, vx_voxel_centre(f.g.off[0], f.g.res, i)));
+  const float d1 = fabsf(VX_FSUB(f.e1, vx_voxel_centre(f.g.off[1], f.g.res, j)));
+  const float d2 = fabsf(VX_FSUB(f.e2, vx_voxel_centre(f.g.off[2], f.g.res, k)));
+  const float dn = normal == 0 ? d0 : d1;
+  const float other = fmaxf(normal == 0 ? d1 : d0, d2);
+  return dn > 1.0001f * other;
+}
+
+// In-face part of candidate rc's ray: fn(x) for every live wave cell x visited after rc that it crosses
+// before it leaves the face, hits an occupied cell or terminates.
+template <class Fn>
+__device__ __forceinline__ void prefix_walk(const Frame& f, const Wave& w, const VisShared& sm, uint32_t rc, Fn fn) {
   int32_t i, j, k;
-  cell_of(f, w, qc, i, j, k);
-  if (occupied(f, sm, i, j, k)) return 0;  // an occupied start cell traverses nothing
+  wave_cell(f, w, sm.rcell[rc], i, j, k);
   VxRay r;
   r.begin(f.g, i, j, k, f.e0, f.e1, f.e2);
   const int32_t normal = w.face == 0 ? 0 : 1;
-  uint32_t marked = 0;
   for (;;) {
-    if (r.next_axis() == normal) break;
-    if (!r.advance()) break;
-    if (!r.inside(f.g)) break;
-    if (occupied(f, sm, r.i, r.j, r.k)) break;
-    const int32_t q = local_of(f, w, r.i, r.j, r.k);
-    if (q > (int32_t)qc) {
-      atomicOr(&target[q >> 5], 1u << (q & 31));
-      ++marked;
-    }
+    if (r.next_axis() == normal) return;
+    if (!r.advance()) return;
+    if (!r.inside(f.g)) return;
+    if (occupied(f, sm, r.i, r.j, r.k)) return;
+    const int32_t x = live_rank(f, w, sm, r.i, r.j, r.k);
+    if (x > (int32_t)rc) fn((uint32_t)x);
   }
-  return marked;
 }
 
-// Phase C for one caster: the reference's occludedBy(), walked once.
-__device__ void trace(const Frame& f, const Wave& w, VisShared& sm, uint32_t qc, unsigned long long& steps) {
-  int32_t i, j, k;
-  cell_of(f, w, qc, i, j, k);
-  const uint32_t tau = w.tau_base + qc;
-  const uint32_t enc = (f.epoch << kEpochShift) | tau;
-  const uint32_t senc = (qc + 2u) << 1;
-  bool hit = false;
-  if (occupied(f, sm, i, j, k)) {  // returns its own index; the caller's assignment memoises it (VoxelGrid.cpp:112)
-    atomicMax(&f.memo[lin(f.g, i, j, k)], enc);
-    atomicMax(&sm.snap[qc], senc);
-    hit = true;
-  } else {
-    VxRay r;
-    r.begin(f.g, i, j, k, f.e0, f.e1, f.e2);
-    uint32_t len = 0;
-    for (;;) {
-      if (!r.inside(f.g)) break;
-      if (occupied(f, sm, r.i, r.j, r.k)) {
-        hit = true;
-        break;
-      }
-      atomicMax(&f.memo[lin(f.g, r.i, r.j, r.k)], enc);
-      const int32_t q = local_of(f, w, r.i, r.j, r.k);
-      if (q >= (int32_t)qc) atomicMax(&sm.snap[q], senc);
-      ++len;
-      if (!r.advance()) break;
-    }
-    steps += len;
-  }
-  f.rayhit[tau] = hit ? 1 : 0;
-  if (hit) atomicOr(&sm.hitbits[qc >> 5], 1u << (qc & 31u));
-}
-
-__device__ void run_wave(const Frame& f, const Wave& w, VisShared& sm, Stats& st) {
-  const uint32_t tid = threadIdx.x;
-  const uint32_t lane = tid & 31u;
-  const uint32_t n = (uint32_t)w.ncols * (uint32_t)f.g.nz;
-
-  if (tid == 0) {
-    sm.n_cand = 0;
-    sm.any_forward = 0;
-    sm.remaining = 0;
-  }
-  if (tid < kWaveCells / 32) {
-    sm.cov_und[tid] = 0;
-    sm.cov_cast[tid] = 0;
-    sm.hitbits[tid] = 0;
-  }
-  long long t0 = clock64();
-  st.waves += 1;
-
-  // ---- A: snapshot + candidates.  All memo loads of a thread are issued before any is consumed.
-  uint32_t m[kCellsPerThread];
-#pragma unroll
-  for (int u = 0; u < kCellsPerThread; ++u) {
-    const uint32_t q = (uint32_t)u * kVisThreads + tid;
-    m[u] = 0;
-    if (q < n) {
-      int32_t i, j, k;
-      cell_of(f, w, q, i, j, k);
-      m[u] = __ldcg(f.memo + lin(f.g, i, j, k));
-    }
-  }
-  __syncthreads();  // n_cand / bitmaps initialised
-  // result of the ray that crossed each already-crossed cell (second, dependent gather)
-  uint32_t h[kCellsPerThread];
-#pragma unroll
-  for (int u = 0; u < kCellsPerThread; ++u) {
-    h[u] = 0;
-    if (m[u] != kDead && (m[u] >> kEpochShift) == f.epoch) h[u] = 2u | (uint32_t)__ldcg(f.rayhit + (m[u] & kTauMask));
-  }
-#pragma unroll
-  for (int u = 0; u < kCellsPerThread; ++u) {
-    const uint32_t q = (uint32_t)u * kVisThreads + tid;
-    bool is_cand = false;
-    if (q < n) {
-      uint32_t s;
-      if (f.inv && m[u] == kDead) {
-        s = kSkip;  // invalid_ == -1: "just skip" (VoxelGrid.cpp:187)
-      } else if (h[u]) {
-        s = h[u];
-      } else {
-        s = 0u;
-        is_cand = true;
-      }
-      sm.snap[q] = s;
-    }
-    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, is_cand);
-    if (ballot) {
+// Phase C: the lanes of the calling warp pull casters from sm.queue and walk the reference's
+// occludedBy() once per ray.
+__device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_t n_cast, uint32_t id_base, Stats& st) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const int32_t normal = w.face == 0 ? 0 : 1;
+  bool active = false, exhausted = false, pending = false, in_face = false;
+  uint32_t pend_word = 0, rc = 0, id = 0, len = 0;
+  VxRay r;
+  for (;;) {
+    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (!exhausted && (idle == 0xFFFFFFFFu || (uint32_t)__popc(idle) >= kRefillLanes)) {
       uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&sm.n_cand, (uint32_t)__popc(ballot));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (is_cand) sm.cand[base + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)q;
+      if (lane == (uint32_t)(__ffs(idle) - 1)) base = atomicAdd(&sm.queue, (uint32_t)__popc(idle));
+      base = __shfl_sync(0xFFFFFFFFu, base, __ffs(idle) - 1);
+      if (base + (uint32_t)__popc(idle) >= n_cast) exhausted = true;
+      if (!active) {
+        const uint32_t s = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        if (s < n_cast) {
+          rc = sm.cand[s];
+          id = id_base + s;
+          int32_t i, j, k;
+          wave_cell(f, w, sm.rcell[rc], i, j, k);
+          r.begin(f.g, i, j, k, f.e0, f.e1, f.e2);
+          active = true;
+          pending = false;
+          in_face = true;
+          len = 0;
+          ++st.rays;
+        }
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, active)) {
+      if (exhausted) break;
+      continue;
+    }
+    if (active) {
+      // cell (r.i, r.j, r.k) is inside the grid.  The caster's own cell is free (live cells are).
+      bool free_cell = true, finished = false, hit = false;
+      if (pending) {
+        pending = false;
+        if (pend_word & 1u) {
+          finished = true;
+          hit = true;
+          free_cell = false;
+        }
+      } else if (len > 0 && coarse_set(f, sm, r.i, r.j, r.k)) {
+        const uint32_t L = lin(f.g, r.i, r.j, r.k);
+        pend_word = __ldg(f.occ + (L >> 5)) >> (L & 31u);  // consumed in the next iteration
+        pending = true;
+        free_cell = false;
+      }
+      if (free_cell) {
+        atomicMax(&f.memo[lin(f.g, r.i, r.j, r.k)], (f.epoch << kEpochShift) | id);
+        if (in_face) {
+          const int32_t x = live_rank(f, w, sm, r.i, r.j, r.k);
+          if (x >= (int32_t)rc) atomicMax(&sm.owner[x], kSet | id);
+          if (r.next_axis() == normal) in_face = false;
+        }
+        ++len;
+        if (!r.advance() || !r.inside(f.g)) finished = true;
+      }
+      if (finished) {
+        if (hit) atomicOr(&f.hitbits[id >> 5], 1u << (id & 31u));
+        st.steps += len;
+        active = false;
+      }
+    }
+  }
+}
+
+// Runs the columns [a, a + range) of one face as far as one wave reaches; returns the columns consumed.
+__device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t a, int32_t range, VisShared& sm, uint32_t& id_base,
+                            Stats& st) {
+  const uint32_t tid = threadIdx.x;
+  long long t0 = clock64();
+  Wave w;
+  w.face = face;
+  w.fixed = fixed;
+  w.a_begin = a;
+
+  // ---- A1: live masks of the chunks of the range, ranks by prefix sum
+  const uint32_t n_chunks = (uint32_t)range * (uint32_t)f.cpc;
+  uint32_t masks[kChunksPerThread];
+  uint32_t local = 0;
+#pragma unroll
+  for (int u = 0; u < kChunksPerThread; ++u) {
+    const uint32_t c = tid * kChunksPerThread + (uint32_t)u;
+    masks[u] = 0;
+    if (c < n_chunks) {
+      uint32_t col, part;
+      if (f.cpc == 1) {
+        col = c;
+        part = 0;
+      } else {
+        col = c / (uint32_t)f.cpc;
+        part = c - col * (uint32_t)f.cpc;
+      }
+      const int32_t outer = a + (int32_t)col;
+      const int32_t i = face == 0 ? fixed : outer, j = face == 0 ? outer : fixed;
+      const uint32_t k0 = part * 32u;
+      const uint32_t len = min(32u, (uint32_t)f.g.nz - k0);
+      masks[u] = extract_bits(f.live, lin(f.g, i, j, (int32_t)k0), len);
+    }
+    local += (uint32_t)__popc(masks[u]);
+  }
+  if (tid == 0) {
+    sm.ncols_ok = 0;
+    sm.any_edge = 0;
+    sm.queue = 0;
+  }
+  uint32_t base = block_scan(sm, local);
+  {
+    uint32_t run = base;
+#pragma unroll
+    for (int u = 0; u < kChunksPerThread; ++u) {
+      const uint32_t c = tid * kChunksPerThread + (uint32_t)u;
+      if (c < n_chunks) {
+        sm.chmask[c] = masks[u];
+        sm.chbase[c] = (uint16_t)(run < 0xFFFFu ? run : 0xFFFFu);
+        run += (uint32_t)__popc(masks[u]);
+        // last chunk of a column: the column fits if the live cells up to and including it do
+        if ((c + 1u) % (uint32_t)f.cpc == 0u && run <= (uint32_t)kMaxLive) atomicMax(&sm.ncols_ok, c / (uint32_t)f.cpc + 1u);
+      }
     }
   }
   __syncthreads();
-  const uint32_t n_cand = sm.n_cand;
+  const uint32_t total_live = sm.scan_total;
+  if (total_live == 0) return range;  // nothing alive in these columns
+  w.ncols = (int32_t)sm.ncols_ok;     // >= 1: one column holds at most nz <= kMaxLive live cells
+  const uint32_t wave_chunks = (uint32_t)w.ncols * (uint32_t)f.cpc;
+  const uint32_t last = wave_chunks - 1u;
+  const uint32_t n_live = (uint32_t)sm.chbase[last] + (uint32_t)__popc(sm.chmask[last]);
+  if (n_live == 0) return w.ncols;
+  st.waves += 1;
+
+  // ---- A2: rank -> cell
+#pragma unroll
+  for (int u = 0; u < kChunksPerThread; ++u) {
+    const uint32_t c = tid * kChunksPerThread + (uint32_t)u;
+    if (c < wave_chunks) {
+      uint32_t m = masks[u];
+      uint32_t r = sm.chbase[c];
+      while (m) {
+        const uint32_t b = (uint32_t)__ffs(m) - 1u;
+        m &= m - 1u;
+        sm.rcell[r++] = (uint16_t)((c << 5) | b);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- A3: snapshot of the memo; candidates in visit order
+  const uint32_t per = (n_live + kVisThreads - 1) / kVisThreads;
+  const uint32_t r_begin = min(n_live, tid * per), r_end = min(n_live, r_begin + per);
+  uint32_t m[kLivePerThread];
+#pragma unroll
+  for (int u = 0; u < kLivePerThread; ++u) {
+    const uint32_t r = r_begin + (uint32_t)u;
+    m[u] = 0;
+    if (r < r_end) {
+      int32_t i, j, k;
+      wave_cell(f, w, sm.rcell[r], i, j, k);
+      m[u] = __ldcg(f.memo + lin(f.g, i, j, k));
+    }
+  }
+  uint32_t cand_flags = 0;
+#pragma unroll
+  for (int u = 0; u < kLivePerThread; ++u) {
+    const uint32_t r = r_begin + (uint32_t)u;
+    if (r < r_end) {
+      if ((m[u] >> kEpochShift) == f.epoch) {
+        sm.owner[r] = kSet | (m[u] & kIdMask);
+      } else {
+        sm.owner[r] = 0;
+        cand_flags |= 1u << u;
+      }
+    }
+  }
+  uint32_t cslot = block_scan(sm, (uint32_t)__popc(cand_flags));
+#pragma unroll
+  for (int u = 0; u < kLivePerThread; ++u)
+    if ((cand_flags >> u) & 1u) sm.cand[cslot++] = (uint16_t)(r_begin + (uint32_t)u);
+  if (tid < kMaxLive / 32) {
+    sm.killed[tid] = 0;
+    sm.decided[tid] = 0;
+    sm.castbit[tid] = 0;
+    sm.has_succ[tid] = 0;
+  }
+  __syncthreads();
+  const uint32_t n_cand = sm.scan_total;
   {
     const long long t1 = clock64();
     st.cyc[0] += (unsigned long long)(t1 - t0);
     t0 = t1;
   }
 
+  uint32_t n_cast = 0;
   if (n_cand > 0) {
-    // ---- B: which candidates cast?
+    const int32_t normal = face == 0 ? 0 : 1;
+    // ---- B0: cnt[x] = candidates visited before x whose in-face ray crosses x
     for (uint32_t p = tid; p < n_cand; p += kVisThreads) {
-      sm.status[p] = 0;
-      if (prefix_mark(f, w, sm, sm.cand[p], sm.cov_und)) sm.any_forward = 1;
+      const uint32_t rc = sm.cand[p];
+      int32_t i, j, k;
+      wave_cell(f, w, sm.rcell[rc], i, j, k);
+      if (normal_first(f, i, j, k, normal)) continue;
+      bool any = false;
+      prefix_walk(f, w, sm, rc, [&](uint32_t x) {
+        if (!(sm.owner[x] & kSet)) {
+          atomicAdd(&sm.owner[x], 1u);
+          any = true;
+        }
+      });
+      if (any) {
+        atomicOr(&sm.has_succ[p >> 5], 1u << (p & 31u));
+        sm.any_edge = 1;
+      }
     }
+    if (tid == 0) sm.undecided = n_cand;
     __syncthreads();
-    if (sm.any_forward) {
+    if (sm.any_edge) {
+      // ---- B1: sweeps until every candidate is decided
       st.resolve_waves += 1;
       for (;;) {
         st.rounds += 1;
-        // decide what can be decided: crossed by a decided caster -> does not cast; crossed by no
-        // undecided candidate -> casts (and marks what it crosses); otherwise wait for a later round
+        uint32_t done = 0;
         for (uint32_t p = tid; p < n_cand; p += kVisThreads) {
-          if (sm.status[p] != 0) continue;
-          const uint32_t qc = sm.cand[p];
-          const uint32_t bit = 1u << (qc & 31u);
-          if (sm.cov_cast[qc >> 5] & bit) {
-            sm.status[p] = 2;
-          } else if (!(sm.cov_und[qc >> 5] & bit)) {
-            sm.status[p] = 1;
-            prefix_mark(f, w, sm, qc, sm.cov_cast);
-          } else {
-            sm.remaining = 1;
+          const uint32_t pbit = 1u << (p & 31u);
+          if (sm.decided[p >> 5] & pbit) continue;
+          const uint32_t rc = sm.cand[p];
+          const bool succ = (sm.has_succ[p >> 5] & pbit) != 0;
+          if ((*(volatile uint32_t*)&sm.killed[rc >> 5] >> (rc & 31u)) & 1u) {
+            atomicOr(&sm.decided[p >> 5], pbit);
+            ++done;
+            if (succ) prefix_walk(f, w, sm, rc, [&](uint32_t x) { if (!(sm.owner[x] & kSet)) atomicSub(&sm.owner[x], 1u); });
+          } else if (*(volatile uint32_t*)&sm.owner[rc] == 0u) {
+            atomicOr(&sm.decided[p >> 5], pbit);
+            atomicOr(&sm.castbit[p >> 5], pbit);
+            ++done;
+            if (succ) prefix_walk(f, w, sm, rc, [&](uint32_t x) { if (!(sm.owner[x] & kSet)) atomicOr(&sm.killed[x >> 5], 1u << (x & 31u)); });
           }
         }
+        if (done) atomicSub(&sm.undecided, done);
         __syncthreads();
-        if (!sm.remaining) break;
+        const uint32_t left = sm.undecided;
         __syncthreads();
-        if (tid == 0) sm.remaining = 0;
-        if (tid < kWaveCells / 32) sm.cov_und[tid] = 0;
-        __syncthreads();
-        for (uint32_t p = tid; p < n_cand; p += kVisThreads)
-          if (sm.status[p] == 0) prefix_mark(f, w, sm, sm.cand[p], sm.cov_und);
-        __syncthreads();
+        if (left == 0) break;
       }
-    } else {
-      for (uint32_t p = tid; p < n_cand; p += kVisThreads) sm.status[p] = 1;
+      // cnt[] back to "unset"; casters compacted in visit order (read everything, then write)
+      const uint32_t cper = (n_cand + kVisThreads - 1) / kVisThreads;
+      const uint32_t p_begin = min(n_cand, tid * cper), p_end = min(n_cand, p_begin + cper);
+      uint16_t keep[kLivePerThread];
+      uint32_t nkeep = 0;
+#pragma unroll
+      for (int u = 0; u < kLivePerThread; ++u) {
+        const uint32_t p = p_begin + (uint32_t)u;
+        keep[u] = 0;
+        if (p < p_end) {
+          const uint32_t rc = sm.cand[p];
+          sm.owner[rc] = 0;
+          if ((sm.castbit[p >> 5] >> (p & 31u)) & 1u) {
+            keep[u] = (uint16_t)(rc | 0x8000u);
+            ++nkeep;
+          }
+        }
+      }
+      uint32_t dst = block_scan(sm, nkeep);  // its barriers separate the reads above from the writes below
+#pragma unroll
+      for (int u = 0; u < kLivePerThread; ++u)
+        if (keep[u] & 0x8000u) sm.cand[dst++] = (uint16_t)(keep[u] & 0x7FFFu);
       __syncthreads();
+      n_cast = sm.scan_total;
+    } else {
+      n_cast = n_cand;
     }
     {
       const long long t1 = clock64();
@@ -380,11 +494,9 @@ __device__ void run_wave(const Frame& f, const Wave& w, VisShared& sm, Stats& st
     }
 
     // ---- C: trace
-    for (uint32_t p = tid; p < n_cand; p += kVisThreads) {
-      if (sm.status[p] != 1) continue;
-      ++st.rays;
-      trace(f, w, sm, sm.cand[p], st.steps);
-    }
+    uint32_t tracers = (n_cast + 47u) / 48u;
+    if (tracers > (uint32_t)kVisWarps) tracers = kVisWarps;
+    if ((tid >> 5) < tracers) trace_warp(f, w, sm, n_cast, id_base, st);
     __syncthreads();
     {
       const long long t1 = clock64();
@@ -394,46 +506,29 @@ __device__ void run_wave(const Frame& f, const Wave& w, VisShared& sm, Stats& st
   }
 
   // ---- D: apply the visit
-  for (int u = 0; u < kCellsPerThread; ++u) {
-    const uint32_t q = (uint32_t)u * kVisThreads + tid;
-    if ((uint32_t)u * kVisThreads + (tid & ~31u) >= n) break;  // warp-uniform
-    bool visited = false, hit = false;
-    uint32_t L = 0;
-    if (q < n) {
-      const uint32_t s = sm.snap[q];
-      if (s != kSkip) {
-        int32_t i, j, k;
-        cell_of(f, w, q, i, j, k);
-        L = lin(f.g, i, j, k);
-        const uint32_t rk = s >> 1;  // 1: crossed before this wave (hit in bit 0); >= 2: in-wave caster rk - 2
-        hit = rk >= 2u ? ((sm.hitbits[(rk - 2u) >> 5] >> ((rk - 2u) & 31u)) & 1u) != 0 : (s & 1u) != 0;
-        visited = true;
-      }
-    }
+  for (uint32_t r = tid; r < n_live; r += kVisThreads) {
+    const uint32_t o = sm.owner[r];
+    const uint32_t id = o & kIdMask;
+    const bool hit = (o & kSet) && ((__ldcg(f.hitbits + (id >> 5)) >> (id & 31u)) & 1u);
+    int32_t i, j, k;
+    wave_cell(f, w, sm.rcell[r], i, j, k);
+    const uint32_t L = lin(f.g, i, j, k);
     if (f.inv) {
-      if (visited && !hit) atomicMax(&f.memo[L], kDead);  // invalid_ = -1, for good
+      if (!hit) atomicAnd(&f.live[L >> 5], ~(1u << (L & 31u)));  // invalid_ = -1, for good
     } else {
-      const uint32_t active = __ballot_sync(0xFFFFFFFFu, visited);
-      if (visited) {
-        const uint32_t word = L >> 5;
-        const uint32_t bit = 1u << (L & 31u);
-        const uint32_t peers = __match_any_sync(active, word);
-        const uint32_t vis = __reduce_or_sync(peers, bit);
-        const uint32_t hits = __reduce_or_sync(peers, hit ? bit : 0u);
-        if ((uint32_t)(__ffs(peers) - 1) == lane) {
-          if (vis != hits) atomicAnd(&f.occl[word], ~(vis & ~hits));
-          if (hits) atomicOr(&f.occl[word], hits);
-        }
-      }
+      if (hit) atomicOr(&f.occl[L >> 5], 1u << (L & 31u));       // last visit wins
+      else atomicAnd(&f.occl[L >> 5], ~(1u << (L & 31u)));
     }
   }
   __syncthreads();
+  id_base += n_cast;
   st.cyc[3] += (unsigned long long)(clock64() - t0);
+  return w.ncols;
 }
 
-__global__ void __launch_bounds__(kVisThreads, 3)
+__global__ void __launch_bounds__(kVisThreads, 6)
 vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restrict__ frames,
-                     const float* __restrict__ endpoints, const VxGridGeom g) {
+                     const float* __restrict__ endpoints, const VxGridGeom g, const uint32_t hit_words) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VisShared& sm = *reinterpret_cast<VisShared*>(smem_raw);
   const VxSlot& slot = slots[blockIdx.x];
@@ -444,28 +539,54 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
 
   Frame f;
   f.g = g;
-  f.nz_shift = ((g.nz & (g.nz - 1)) == 0) ? (31 - __clz(g.nz)) : -1;
+  f.cpc = (g.nz + 31) >> 5;
   f.occ = slot.occ;
+  f.live = slot.alive;
   f.memo = slot.memo;
-  f.rayhit = slot.rayhit;
+  f.hitbits = slot.hitbits;
   f.occl = slot.occl;
-  {
-    const uint32_t cx = (uint32_t)(g.nx + 3) >> 2, cy = (uint32_t)(g.ny + 3) >> 2, cz = (uint32_t)(g.nz + 1) >> 1;
-    if ((cx * cy * cz + 31u) / 32u <= kCoarseWordsMax) {
-      f.cy = (int32_t)cy;
-      f.cz = (int32_t)cz;
-    } else {
-      f.cy = f.cz = 0;  // grid too large for the shared-memory index: test the L2-resident bitmap directly
+  f.cshift = -1;
+  f.cyb = 0;
+  for (int32_t s = 0; s < 8; ++s) {
+    const uint64_t cxb = (uint64_t)((g.nx + (1 << s) - 1) >> s), cyb = (uint64_t)((g.ny + (1 << s) - 1) >> s);
+    if (cxb * cyb * (uint64_t)g.nz <= (uint64_t)kCoarseWords * 32u) {
+      f.cshift = s;
+      f.cyb = (int32_t)cyb;
+      break;
     }
   }
-  if (f.cz > 0) build_sparse_occupancy(f, sm);
+
+  // coarse occupancy; live = free cells; occluded starts as "occupied"; no ray has a hit bit yet
+  for (uint32_t x = tid; x < kCoarseWords; x += kVisThreads) sm.coarse[x] = 0;
+  __syncthreads();
+  for (uint32_t x = tid; x < words; x += kVisThreads) {
+    const uint32_t o = __ldg(f.occ + x);
+    const uint32_t valid = (x == words - 1u && (nvox & 31u)) ? ((1u << (nvox & 31u)) - 1u) : 0xFFFFFFFFu;
+    f.live[x] = ~o & valid;
+    f.occl[x] = o;
+    if (o && f.cshift >= 0) {
+      if (g.nz == 32) {  // one word = one column
+        const uint32_t i = x / (uint32_t)g.ny, j = x - i * (uint32_t)g.ny;
+        atomicOr(&sm.coarse[(i >> f.cshift) * (uint32_t)f.cyb + (j >> f.cshift)], o);
+      } else {
+        uint32_t bits = o;
+        while (bits) {
+          const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+          bits &= bits - 1u;
+          const uint32_t L = x * 32u + b;
+          const uint32_t k = L % (uint32_t)g.nz, ij = L / (uint32_t)g.nz;
+          const uint32_t i = ij / (uint32_t)g.ny, j = ij - i * (uint32_t)g.ny;
+          const uint32_t C = ((i >> f.cshift) * (uint32_t)f.cyb + (j >> f.cshift)) * (uint32_t)g.nz + k;
+          atomicOr(&sm.coarse[C >> 5], 1u << (C & 31u));
+        }
+      }
+    }
+  }
+  for (uint32_t x = tid; x < hit_words; x += kVisThreads) f.hitbits[x] = 0;
 
   Stats st;
   const int32_t shells = vx_num_shells(g.nx, g.ny);
-  int32_t cols_per_wave = kWaveCells / g.nz;
-  if (cols_per_wave < 1) cols_per_wave = 1;
-
-  for (uint32_t w = tid; w < words; w += kVisThreads) f.occl[w] = 0u;
+  const int32_t max_cols = kMaxChunks / f.cpc;
 
   const uint32_t n_pass = 1u + vf.n_endpoints;
   for (uint32_t pass = 0; pass < n_pass; ++pass) {
@@ -479,43 +600,29 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
       f.e2 = e[2];
     }
     f.epoch = (pass % kMaxEpoch) + 1u;
-    if (pass == 0) {
+    if (pass % kMaxEpoch == 0) {  // first pass, or the epoch counter restarts: forget every memo
       for (uint32_t x = tid; x < nvox; x += kVisThreads) f.memo[x] = 0u;
-    } else if (pass % kMaxEpoch == 0) {  // epoch counter restarts: forget every memo but keep the dead cells
-      for (uint32_t x = tid; x < nvox; x += kVisThreads)
-        if (__ldcg(f.memo + x) != kDead) f.memo[x] = 0u;
     }
     __syncthreads();
 
-    uint32_t tau = 0;
+    uint32_t id_base = 0;
     for (int32_t o = 0; o < shells; ++o) {
       for (int32_t face = 0; face < 3; ++face) {
         const int32_t outer = face == 0 ? g.ny : g.nx - o - 1;
-        Wave w;
-        w.face = face;
-        w.fixed = face == 0 ? g.nx - 1 - o : (face == 1 ? o : g.ny - 1 - o);
-        for (int32_t a = 0; a < outer; a += cols_per_wave) {
-          w.a_begin = a;
-          w.ncols = outer - a < cols_per_wave ? outer - a : cols_per_wave;
-          w.tau_base = tau;
-          run_wave(f, w, sm, st);
-          tau += (uint32_t)w.ncols * (uint32_t)g.nz;
+        const int32_t fixed = face == 0 ? g.nx - 1 - o : (face == 1 ? o : g.ny - 1 - o);
+        for (int32_t a = 0; a < outer;) {
+          const int32_t range = outer - a < max_cols ? outer - a : max_cols;
+          a += run_wave(f, face, fixed, a, range, sm, id_base, st);
         }
       }
     }
+    // the ray ids start again at 0: clear the hit bits this pass used
+    const uint32_t used_words = min(hit_words, (id_base + 31u) >> 5);
+    for (uint32_t x = tid; x < used_words; x += kVisThreads) f.hitbits[x] = 0;
     if (pass == 0) {  // invalid_ = occlusions_ (VoxelGrid.cpp:169): what is not occluded is dead from here on
-      for (uint32_t x = tid; x < nvox; x += kVisThreads)
-        if (!((__ldcg(f.occl + (x >> 5)) >> (x & 31u)) & 1u)) f.memo[x] = kDead;
-      __syncthreads();
+      for (uint32_t x = tid; x < words; x += kVisThreads) f.live[x] = __ldcg(f.occl + x) & ~__ldg(f.occ + x);
     }
-  }
-
-  // alive bitmap for the packer: invalid_ != -1
-  for (uint32_t x0 = 0; x0 < words * 32u; x0 += kVisThreads) {
-    const uint32_t x = x0 + tid;
-    const bool alive = x < nvox && __ldcg(f.memo + x) != kDead;
-    const uint32_t word = __ballot_sync(0xFFFFFFFFu, alive);
-    if ((tid & 31u) == 0 && (x >> 5) < words) slot.alive[x >> 5] = word;
+    __syncthreads();
   }
 
   // statistics: rays / steps summed over threads, the rest as seen by thread 0
@@ -545,7 +652,8 @@ cudaError_t vx_visibility_prepare() {
 cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, uint32_t n_slots,
                                  const float* endpoints, VxGridGeom geom, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
-  vx_visibility_kernel<<<n_slots, kVisThreads, sizeof(VisShared), stream>>>(slots, frames, endpoints, geom);
+  const uint32_t hit_words = (uint32_t)(vx_visibility_visits(geom) / 32u + 1u);
+  vx_visibility_kernel<<<n_slots, kVisThreads, sizeof(VisShared), stream>>>(slots, frames, endpoints, geom, hit_words);
   return cudaGetLastError();
 }
 
