@@ -49,7 +49,7 @@ class FilterDesc(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("frames_in_flight", C.c_uint32), ("table_log2_capacity", C.c_uint32), ("stream", C.c_void_p),
-                ("debug", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("debug", C.c_uint32), ("table_sets", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
 class FrameDesc(C.Structure):

@@ -23,13 +23,26 @@ struct DeviceScan {
   uint32_t n = 0;
 };
 
-struct SlotMem {
+// Histogram tables + vote arrays: shared by the frames of a batch that are `table_sets` apart.
+struct TableSet {
   void* arena = nullptr;
-  size_t bytes = 0;
-  VxSlot dev{};  // device pointers
+  VxTable input{}, target{};
+  unsigned long long* best_input = nullptr;
+  unsigned long long* best_target = nullptr;
 };
 
-enum { EV_BEGIN = 0, EV_FILL, EV_VOTE, EV_EMIT, EV_VIS, EV_PACK, EV_END, EV_COUNT };
+// Per-frame state that outlives fill -> vote -> emit: bitmaps and the four output images.
+struct FrameRec {
+  void* arena = nullptr;
+  VxSlot dev{};  // device pointers (tables filled in from the frame's table set)
+};
+
+struct ScratchMem {
+  void* arena = nullptr;
+  VxVisScratch dev{};
+};
+
+enum { EV_BEGIN = 0, EV_VIS_BEGIN, EV_VIS, EV_PACK, EV_END, EV_COUNT };
 
 // per-slot counter block (uint32 words): used/overflow of both tables, then two 64-bit statistics
 constexpr size_t kCounterWords = 4 + 2 * VX_SLOT_STATS + 2;  // 24 words = 96 bytes per slot
@@ -51,16 +64,21 @@ struct vx_ctx {
 
   std::unordered_map<uint32_t, DeviceScan> scans;
 
-  uint32_t max_slots = 0;
+  uint32_t max_slots = 0;   // frames per batch (one visibility launch)
+  uint32_t table_sets = 0;  // frames per fill -> vote -> emit launch
   uint32_t log2_target = 21, log2_input = 18;
   bool keep_tables = false;
   bool tables_dirty = false;  // tables hold the previous batch (debug mode)
   uint32_t dirty_slots = 0;
-  std::vector<SlotMem> slots;
+  std::vector<TableSet> tables;
+  std::vector<FrameRec> slots;
+  std::vector<ScratchMem> scratch;  // one per resident visibility CTA
+  VxVisScratch* d_scratch = nullptr;
+  uint32_t* d_locks = nullptr;
   VxSlot* d_slots = nullptr;
-  uint32_t d_slots_cap = 0;
   uint32_t* d_counters = nullptr;  // max_slots * kCounterWords
   uint32_t* h_counters = nullptr;  // pinned mirror
+  std::vector<cudaEvent_t> ev_sub;  // 4 per fill -> vote -> emit launch
 
   // batch staging (items, ap, endpoints, vis frames): pinned host + device mirror
   unsigned char* h_stage = nullptr;
@@ -114,70 +132,97 @@ size_t table_bytes(uint32_t log2_cap) {
   return align_up(cap * 8, 256) + align_up(cap * 4, 256) + align_up(cap * 4, 256);
 }
 
-size_t slot_bytes(const vx_ctx* c) {
-  const size_t nv = c->nvox, w = c->words;
-  return table_bytes(c->log2_target) + table_bytes(c->log2_input) + 2 * align_up(nv * 8, 256) + 3 * align_up((size_t)w * 4, 256) +
-         align_up(nv * 4, 256) + align_up(nv * 2, 256) + 3 * align_up((size_t)w * 4, 256) + align_up((c->visits / 32 + 1) * 4, 256);
+size_t table_set_bytes(const vx_ctx* c) {
+  return table_bytes(c->log2_target) + table_bytes(c->log2_input) + 2 * align_up(c->nvox * 8, 256);
 }
 
-int alloc_slot(vx_ctx* c, uint32_t index) {
-  SlotMem& s = c->slots[index];
-  s.bytes = slot_bytes(c);
-  VX_CUDA(c, cudaMalloc(&s.arena, s.bytes));
-  unsigned char* p = static_cast<unsigned char*>(s.arena);
-  auto take = [&](size_t bytes) {
+size_t frame_bytes(const vx_ctx* c) { return 6 * align_up((size_t)c->words * 4, 256) + align_up(c->nvox * 2, 256); }
+
+size_t scratch_bytes(const vx_ctx* c) { return align_up(c->nvox * 4, 256) + align_up((c->visits / 32 + 1) * 4, 256); }
+
+struct Carver {
+  unsigned char* p;
+  unsigned char* take(size_t bytes) {
     unsigned char* r = p;
     p += align_up(bytes, 256);
     return r;
-  };
-  auto carve_table = [&](VxTable& t, uint32_t log2_cap, uint32_t* counters) {
+  }
+};
+
+int alloc_table_set(vx_ctx* c, TableSet& t) {
+  VX_CUDA(c, cudaMalloc(&t.arena, table_set_bytes(c)));
+  Carver cv{static_cast<unsigned char*>(t.arena)};
+  auto carve = [&](VxTable& tb, uint32_t log2_cap) {
     const size_t cap = (size_t)1 << log2_cap;
-    t.keys = reinterpret_cast<unsigned long long*>(take(cap * 8));
-    t.counts = reinterpret_cast<uint32_t*>(take(cap * 4));
-    t.used = reinterpret_cast<uint32_t*>(take(cap * 4));
-    t.used_count = counters;
-    t.overflow = counters + 1;
-    t.log2_cap = log2_cap;
+    tb.keys = reinterpret_cast<unsigned long long*>(cv.take(cap * 8));
+    tb.counts = reinterpret_cast<uint32_t*>(cv.take(cap * 4));
+    tb.used = reinterpret_cast<uint32_t*>(cv.take(cap * 4));
+    tb.log2_cap = log2_cap;
+    return cap;
   };
+  const size_t cap_t = carve(t.target, c->log2_target), cap_i = carve(t.input, c->log2_input);
+  t.best_input = reinterpret_cast<unsigned long long*>(cv.take(c->nvox * 8));
+  t.best_target = reinterpret_cast<unsigned long long*>(cv.take(c->nvox * 8));
+  // empty tables, empty vote arrays (vote / emit leave them empty again)
+  VX_CUDA(c, cudaMemsetAsync(t.target.keys, 0xFF, cap_t * 8, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(t.target.counts, 0, cap_t * 4, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(t.input.keys, 0xFF, cap_i * 8, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(t.input.counts, 0, cap_i * 4, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(t.best_input, 0, c->nvox * 8, c->stream));
+  VX_CUDA(c, cudaMemsetAsync(t.best_target, 0, c->nvox * 8, c->stream));
+  return VX_OK;
+}
+
+int alloc_frame(vx_ctx* c, uint32_t index) {
+  FrameRec& s = c->slots[index];
+  VX_CUDA(c, cudaMalloc(&s.arena, frame_bytes(c)));
+  Carver cv{static_cast<unsigned char*>(s.arena)};
+  const TableSet& t = c->tables[index % c->table_sets];
   uint32_t* cnt = c->d_counters + (size_t)index * kCounterWords;
-  carve_table(s.dev.target, c->log2_target, cnt + 0);
-  carve_table(s.dev.input, c->log2_input, cnt + 2);
+  s.dev.target = t.target;
+  s.dev.target.used_count = cnt + 0;
+  s.dev.target.overflow = cnt + 1;
+  s.dev.input = t.input;
+  s.dev.input.used_count = cnt + 2;
+  s.dev.input.overflow = cnt + 3;
   s.dev.counters = reinterpret_cast<unsigned long long*>(cnt + 4);
-  s.dev.best_input = reinterpret_cast<unsigned long long*>(take(c->nvox * 8));
-  s.dev.best_target = reinterpret_cast<unsigned long long*>(take(c->nvox * 8));
-  s.dev.occ = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
-  s.dev.occl = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
-  s.dev.alive = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
-  s.dev.memo = reinterpret_cast<uint32_t*>(take(c->nvox * 4));
-  s.dev.hitbits = reinterpret_cast<uint32_t*>(take((c->visits / 32 + 1) * 4));
-  s.dev.out_label = reinterpret_cast<uint16_t*>(take(c->nvox * 2));
-  s.dev.out_bin = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
-  s.dev.out_occluded = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
-  s.dev.out_invalid = reinterpret_cast<uint32_t*>(take((size_t)c->words * 4));
-  // empty tables, empty vote arrays
-  const size_t cap_t = (size_t)1 << c->log2_target, cap_i = (size_t)1 << c->log2_input;
-  VX_CUDA(c, cudaMemsetAsync(s.dev.target.keys, 0xFF, cap_t * 8, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(s.dev.target.counts, 0, cap_t * 4, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(s.dev.input.keys, 0xFF, cap_i * 8, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(s.dev.input.counts, 0, cap_i * 4, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(s.dev.best_input, 0, c->nvox * 8, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(s.dev.best_target, 0, c->nvox * 8, c->stream));
+  s.dev.best_input = t.best_input;
+  s.dev.best_target = t.best_target;
+  s.dev.occ = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
+  s.dev.occl = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
+  s.dev.alive = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
+  s.dev.out_label = reinterpret_cast<uint16_t*>(cv.take(c->nvox * 2));
+  s.dev.out_bin = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
+  s.dev.out_occluded = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
+  s.dev.out_invalid = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
   return VX_OK;
 }
 
 void free_slots(vx_ctx* c) {
-  for (SlotMem& s : c->slots)
+  for (FrameRec& s : c->slots)
     if (s.arena) cudaFree(s.arena);
   c->slots.clear();
+  for (TableSet& t : c->tables)
+    if (t.arena) cudaFree(t.arena);
+  c->tables.clear();
   c->tables_dirty = false;
 }
 
 int ensure_slots(vx_ctx* c, uint32_t n) {
+  const uint32_t want_sets = n < c->table_sets ? n : c->table_sets;
+  while (c->tables.size() < want_sets) {
+    c->tables.emplace_back();
+    const int rc = alloc_table_set(c, c->tables.back());
+    if (rc != VX_OK) {
+      c->tables.pop_back();
+      return rc;
+    }
+  }
   if (c->slots.size() >= n) return VX_OK;
   const size_t old = c->slots.size();
   c->slots.resize(n);
   for (size_t i = old; i < n; ++i) {
-    const int rc = alloc_slot(c, (uint32_t)i);
+    const int rc = alloc_frame(c, (uint32_t)i);
     if (rc != VX_OK) {
       c->slots.resize(i);
       return rc;
@@ -186,6 +231,33 @@ int ensure_slots(vx_ctx* c, uint32_t n) {
   std::vector<VxSlot> host(n);
   for (size_t i = 0; i < n; ++i) host[i] = c->slots[i].dev;
   VX_CUDA(c, cudaMemcpyAsync(c->d_slots, host.data(), n * sizeof(VxSlot), cudaMemcpyHostToDevice, c->stream));
+  VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  return VX_OK;
+}
+
+// scratch buffers of the visibility kernel: one per CTA the device can hold (at most n_frames)
+int ensure_scratch(vx_ctx* c, uint32_t n_frames) {
+  uint32_t want = (uint32_t)vx_visibility_resident_ctas(c->device);
+  if (want == 0) return fail(c, VX_ERR_CUDA, "the visibility kernel does not fit on this device");
+  if (!c->d_scratch) {
+    VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_scratch), (size_t)want * sizeof(VxVisScratch)));
+    VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_locks), (size_t)want * sizeof(uint32_t)));
+    VX_CUDA(c, cudaMemsetAsync(c->d_locks, 0, (size_t)want * sizeof(uint32_t), c->stream));
+  }
+  if (want > n_frames) want = n_frames;
+  if (c->scratch.size() >= want) return VX_OK;
+  const size_t old = c->scratch.size();
+  c->scratch.resize(want);
+  for (size_t i = old; i < want; ++i) {
+    ScratchMem& m = c->scratch[i];
+    VX_CUDA(c, cudaMalloc(&m.arena, scratch_bytes(c)));
+    Carver cv{static_cast<unsigned char*>(m.arena)};
+    m.dev.memo = reinterpret_cast<uint32_t*>(cv.take(c->nvox * 4));
+    m.dev.hitbits = reinterpret_cast<uint32_t*>(cv.take((c->visits / 32 + 1) * 4));
+  }
+  std::vector<VxVisScratch> host(want);
+  for (size_t i = 0; i < want; ++i) host[i] = c->scratch[i].dev;
+  VX_CUDA(c, cudaMemcpyAsync(c->d_scratch, host.data(), (size_t)want * sizeof(VxVisScratch), cudaMemcpyHostToDevice, c->stream));
   VX_CUDA(c, cudaStreamSynchronize(c->stream));
   return VX_OK;
 }
@@ -209,6 +281,8 @@ int ensure_stage(vx_ctx* c, size_t bytes) {
 int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   int rc = ensure_slots(c, nb);
   if (rc != VX_OK) return rc;
+  rc = ensure_scratch(c, nb);
+  if (rc != VX_OK) return rc;
 
   // ---- stage the batch description
   size_t n_items = 0, n_ap = 0, n_ep = 0;
@@ -230,10 +304,12 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   VxVisFrame* vis = reinterpret_cast<VxVisFrame*>(c->h_stage + off_vis);
 
   size_t ii = 0, ai = 0, ei = 0;
-  uint32_t max_points = 0;
   uint64_t points = 0;
+  std::vector<size_t> item_begin(nb + 1, 0);
+  std::vector<uint32_t> frame_max_points(nb, 0);
   for (uint32_t f = 0; f < nb; ++f) {
     const vx_frame_desc& fr = frames[f];
+    item_begin[f] = ii;
     if ((fr.n_prior && (!fr.prior_ids || !fr.ap_prior)) || (fr.n_past && (!fr.past_ids || !fr.ap_past)) || (fr.n_endpoints && !fr.endpoints))
       return fail(c, VX_ERR_INVALID, "frame descriptor has null arrays");
     for (int part = 0; part < 2; ++part) {
@@ -252,7 +328,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
         item.both = part == 0 ? 1u : 0u;
         std::memcpy(ap + 16 * ai, aps + 16 * (size_t)s, 16 * sizeof(float));
         ++ai;
-        if (item.n > max_points) max_points = item.n;
+        if (item.n > frame_max_points[f]) frame_max_points[f] = item.n;
         points += item.n;
       }
     }
@@ -261,6 +337,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     if (fr.n_endpoints) std::memcpy(ep + 3 * ei, fr.endpoints, (size_t)fr.n_endpoints * 3 * sizeof(float));
     ei += fr.n_endpoints;
   }
+  item_begin[nb] = ii;
 
   cudaStream_t st = c->stream;
   if (c->tables_dirty) {  // debug mode kept the previous batch's tables
@@ -275,14 +352,31 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   const float* d_ep = reinterpret_cast<const float*>(c->d_stage + off_ep);
   const VxVisFrame* d_vis = reinterpret_cast<const VxVisFrame*>(c->d_stage + off_vis);
 
+  // fill -> vote -> emit in groups of `table_sets` frames (frames of different groups share tables)
+  const uint32_t n_sub = (nb + c->table_sets - 1) / c->table_sets;
+  while (c->ev_sub.size() < (size_t)n_sub * 4) {
+    cudaEvent_t e;
+    VX_CUDA(c, cudaEventCreate(&e));
+    c->ev_sub.push_back(e);
+  }
+  uint64_t fill_launches = 0;
   VX_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], st));
-  VX_CUDA(c, vx_launch_fill(d_items, (uint32_t)n_items, max_points, d_ap, c->d_slots, c->geom, c->filter, st));
-  VX_CUDA(c, cudaEventRecord(c->ev[EV_FILL], st));
-  VX_CUDA(c, vx_launch_vote(c->d_slots, nb, c->keep_tables ? 1 : 0, st));
-  VX_CUDA(c, cudaEventRecord(c->ev[EV_VOTE], st));
-  VX_CUDA(c, vx_launch_emit(c->d_slots, nb, c->nvox, st));
-  VX_CUDA(c, cudaEventRecord(c->ev[EV_EMIT], st));
-  VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, st));
+  for (uint32_t g = 0; g < n_sub; ++g) {
+    const uint32_t f0 = g * c->table_sets, f1 = f0 + c->table_sets < nb ? f0 + c->table_sets : nb;
+    uint32_t max_points = 0;
+    for (uint32_t f = f0; f < f1; ++f) max_points = frame_max_points[f] > max_points ? frame_max_points[f] : max_points;
+    const uint32_t n_sub_items = (uint32_t)(item_begin[f1] - item_begin[f0]);
+    VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 0], st));
+    VX_CUDA(c, vx_launch_fill(d_items + item_begin[f0], n_sub_items, max_points, d_ap, c->d_slots, c->geom, c->filter, st));
+    VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 1], st));
+    VX_CUDA(c, vx_launch_vote(c->d_slots + f0, f1 - f0, c->keep_tables ? 1 : 0, st));
+    VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 2], st));
+    VX_CUDA(c, vx_launch_emit(c->d_slots + f0, f1 - f0, c->nvox, st));
+    VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 3], st));
+    fill_launches += (n_sub_items + 65534) / 65535;
+  }
+  VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS_BEGIN], st));
+  VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, c->d_scratch, (uint32_t)c->scratch.size(), c->d_locks, st));
   VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS], st));
   VX_CUDA(c, vx_launch_pack(c->d_slots, nb, c->nvox, st));
   VX_CUDA(c, cudaEventRecord(c->ev[EV_PACK], st));
@@ -321,17 +415,23 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]);
     return (double)ms;
   };
-  c->times.fill_ms += span(EV_BEGIN, EV_FILL);
-  c->times.vote_ms += span(EV_FILL, EV_VOTE);
-  c->times.emit_ms += span(EV_VOTE, EV_EMIT);
-  c->times.visibility_ms += span(EV_EMIT, EV_VIS);
+  for (uint32_t g = 0; g < n_sub; ++g) {
+    auto sub = [&](int a, int b) {
+      cudaEventElapsedTime(&ms, c->ev_sub[4 * g + a], c->ev_sub[4 * g + b]);
+      return (double)ms;
+    };
+    c->times.fill_ms += sub(0, 1);
+    c->times.vote_ms += sub(1, 2);
+    c->times.emit_ms += sub(2, 3);
+  }
+  c->times.visibility_ms += span(EV_VIS_BEGIN, EV_VIS);
   c->times.pack_ms += span(EV_VIS, EV_PACK);
   c->times.total_ms += span(EV_BEGIN, EV_END);
   c->times.frames += nb;
   c->times.points_read += points;
-  c->times.fill_launches += (n_items + 65534) / 65535;
-  c->times.vote_launches += 1;
-  c->times.emit_launches += 1;
+  c->times.fill_launches += fill_launches;
+  c->times.vote_launches += n_sub;
+  c->times.emit_launches += n_sub;
   c->times.visibility_launches += 1;
   c->times.pack_launches += 1;
   c->times.rays_cast += stats[0];
@@ -446,13 +546,29 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   if (c->log2_target > 30) c->log2_target = 30;
   c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
 
+  // Sizing.  A batch = the frames of ONE visibility launch (one CTA per frame, scheduled by the hardware
+  // as resident CTAs retire); its histogram tables are shared by frames `table_sets` apart.
+  const uint32_t resident = (uint32_t)vx_visibility_resident_ctas(device);
+  if (resident == 0) {
+    c->error = "the visibility kernel does not fit on this device";
+    return bail(VX_ERR_CUDA);
+  }
+  c->table_sets = options && options->table_sets ? options->table_sets : 32u;
   size_t free_b = 0, total_b = 0;
   VX_CREATE_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  uint32_t want = options && options->frames_in_flight ? options->frames_in_flight : 296u;
-  const size_t per_slot = slot_bytes(c);
-  const size_t budget = free_b / 2;
-  if ((size_t)want * per_slot > budget) want = (uint32_t)(budget / per_slot);
+  uint32_t want = options && options->frames_in_flight ? options->frames_in_flight : 4u * resident;
+  if (c->keep_tables && want > 8u && !(options && options->frames_in_flight)) want = 8u;  // debug: small batches,
+  if (c->keep_tables || want < c->table_sets) c->table_sets = want;                       // every frame its own tables
+  {
+    const size_t fixed = (size_t)resident * scratch_bytes(c) + (size_t)c->table_sets * table_set_bytes(c);
+    const size_t budget = free_b / 10 * 7;
+    const size_t left = budget > fixed ? budget - fixed : 0;
+    const size_t fit = left / frame_bytes(c);
+    if ((size_t)want > fit) want = (uint32_t)fit;
+  }
+  if (want > 65535u) want = 65535u;
   if (want < 1) want = 1;
+  if (c->table_sets > want) c->table_sets = want;
   c->max_slots = want;
   VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_slots), (size_t)want * sizeof(VxSlot)));
   VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_counters), (size_t)want * kCounterWords * sizeof(uint32_t)));
@@ -471,6 +587,11 @@ void vx_destroy(vx_ctx* c) {
     cudaFree(kv.second.points);
     cudaFree(kv.second.labels);
   }
+  for (ScratchMem& m : c->scratch)
+    if (m.arena) cudaFree(m.arena);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->d_locks) cudaFree(c->d_locks);
+  for (cudaEvent_t e : c->ev_sub) cudaEventDestroy(e);
   if (c->d_slots) cudaFree(c->d_slots);
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -540,8 +661,12 @@ int vx_evict_all(vx_ctx* c) {
 int vx_process_frames(vx_ctx* c, const vx_frame_desc* frames, uint32_t n) {
   if (!c || (n && !frames)) return fail(c, VX_ERR_INVALID, "null argument");
   VX_CUDA(c, cudaSetDevice(c->device));
+  // batches of equal size (a short last batch would leave most of the device idle for a whole batch time)
+  const uint32_t n_batches = n ? (n + c->max_slots - 1) / c->max_slots : 0;
+  const uint32_t per_batch = n_batches ? (n + n_batches - 1) / n_batches : 0;
   for (uint32_t base = 0; base < n;) {
-    const uint32_t nb = n - base < c->max_slots ? n - base : c->max_slots;
+    uint32_t nb = n - base < per_batch ? n - base : per_batch;
+    if (nb > c->max_slots) nb = c->max_slots;
     int rc = run_batch(c, frames + base, nb);
     if (rc == VX_ERR_TABLE_OVERFLOW) {
       // grow the histogram tables (x4) and redo this batch
@@ -550,12 +675,9 @@ int vx_process_frames(vx_ctx* c, const vx_frame_desc* frames, uint32_t n) {
       free_slots(c);
       c->log2_target += 2;
       c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
-      const size_t per_slot = slot_bytes(c);
       size_t free_b = 0, total_b = 0;
       VX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-      uint32_t fit = (uint32_t)((free_b / 2) / per_slot);
-      if (fit < 1) fit = 1;
-      if (fit < c->max_slots) c->max_slots = fit;
+      while (c->table_sets > 1 && (size_t)c->table_sets * table_set_bytes(c) > free_b / 2) c->table_sets /= 2;
       continue;
     }
     if (rc != VX_OK) return rc;

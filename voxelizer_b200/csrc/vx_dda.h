@@ -53,11 +53,14 @@ VX_HD int32_t vx_trunc_i32(float f) {
   return (int32_t)f;
 }
 
-// VoxelGrid.h:93-97: float(double(float(off + float(i*res))) + 0.5*double(res))
+// VoxelGrid.h:93-97: float(double(float(off + float(i*res))) + 0.5*double(res)).
+// The reference adds in double and narrows.  Both operands are floats (0.5*res is exact), and a
+// double holds 53 >= 2*24 + 2 bits, so rounding the double sum to float gives the correctly rounded
+// float sum (double rounding is innocuous for + - * / at that width): one fp32 add is bit-identical.
 VX_HD float vx_voxel_centre(float off, float res, int32_t i) {
   const float a = VX_FMUL(VX_I2F(i), res);
   const float b = VX_FADD(off, a);
-  return VX_D2F(VX_DADD((double)b, VX_DMUL(0.5, (double)res)));
+  return VX_FADD(b, VX_FMUL(0.5f, res));
 }
 
 // Per-axis traversal constants (VoxelGrid.cpp:249-270).
@@ -69,21 +72,23 @@ struct VxAxis {
   int32_t end;   // end-voxel coordinate: truncation toward zero (VoxelGrid.h:99-102)
 };
 
+// NextCrossingT = float(+-half / double(dir)) with half = 0.5 * double(res) (VoxelGrid.cpp:257,264): by
+// the same argument the double division narrowed to float equals the fp32 division (0.5f*res) / dir,
+// and because halving is exact that is 0.5f * DeltaT unless DeltaT is subnormal (then divide again).
 VX_HD VxAxis vx_axis_setup(float off, float res, int32_t size, int32_t start, float endpoint) {
   VxAxis a;
   const float dir = VX_FSUB(endpoint, vx_voxel_centre(off, res, start));
-  const double half = VX_DMUL(0.5, (double)res);
   if (dir < 0.0f) {
-    a.tmax = VX_D2F(VX_DDIV(-half, (double)dir));
     a.tdelta = VX_FDIV(-res, dir);
     a.step = -1;
     a.out = 0;
   } else {
-    a.tmax = VX_D2F(VX_DDIV(half, (double)dir));
     a.tdelta = VX_FDIV(res, dir);
     a.step = 1;
     a.out = size;
   }
+  a.tmax = VX_FMUL(0.5f, a.tdelta);
+  if (a.tdelta < 4.0e-38f) a.tmax = dir < 0.0f ? VX_FDIV(VX_FMUL(-0.5f, res), dir) : VX_FDIV(VX_FMUL(0.5f, res), dir);
   a.end = vx_trunc_i32(VX_FDIV(VX_FSUB(endpoint, off), res));
   return a;
 }
@@ -140,7 +145,10 @@ struct VxRay {
     tz = a2 ? nz_ : tz;
     const int32_t pos = a0 ? i : (a1 ? j : k);
     const int32_t out = a0 ? ox : (a1 ? oy : oz);
-    if (pos == out) return false;
+    // pos == out: the reference's break after the step.  pos < 0 (a negative step out of layer 0, which
+    // `out == 0` does not catch) ends the reference loop at the top of its next iteration (VoxelGrid.cpp:286).
+    // Either way nothing more is traversed and the ray misses: after `true` the position is inside the grid.
+    if (pos == out || pos < 0) return false;
     if (i == ex && j == ey && k == ez) return false;
     return true;
   }

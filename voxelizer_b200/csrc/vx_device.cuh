@@ -27,7 +27,8 @@ struct VxTable {
   uint32_t log2_cap;
 };
 
-// One frame slot: everything a frame in flight needs on the device.
+// One frame of a batch.  The histogram tables / vote arrays are shared by frames that are `table_sets`
+// apart (they are processed by different fill -> vote -> emit launches); the rest is per frame.
 struct VxSlot {
   VxTable input;              // priorGrid histogram
   VxTable target;             // pastGrid histogram
@@ -36,13 +37,18 @@ struct VxSlot {
   uint32_t* occ;              // [words] target grid occupancy (count > 0), bit L
   uint32_t* occl;             // [words] occlusions_ > -1
   uint32_t* alive;            // [words] free cells with invalid_ != -1 (the traversal's live set)
-  uint32_t* memo;             // [nvox]  occludedBy_ as (pass epoch << 25 | id of the latest ray that crossed the cell)
-  uint32_t* hitbits;          // [visits / 32 + 1] ray id -> the ray ended on an occupied cell (current pass)
   uint16_t* out_label;        // [nvox]
   uint32_t* out_bin;          // [words] MSB-first packed
   uint32_t* out_occluded;     // [words]
   uint32_t* out_invalid;      // [words]
   unsigned long long* counters;  // [VX_SLOT_STATS] rays, steps, waves, resolve waves, rounds, cycles[4]
+};
+
+// Scratch of one RESIDENT visibility CTA (claimed at run time, so the pool is as large as the number
+// of CTAs the device can hold, not as the number of frames of a batch).
+struct VxVisScratch {
+  uint32_t* memo;     // [nvox]  occludedBy_ as (pass epoch << 25 | id of the latest ray that crossed the cell)
+  uint32_t* hitbits;  // [visits / 32 + 1] ray id -> the ray ended on an occupied cell (current pass)
 };
 
 // One (frame, scan) unit of fill work.

@@ -16,10 +16,13 @@ cudaError_t vx_launch_table_reset(const VxSlot* slots, uint32_t n_slots, cudaStr
 // K5a: best -> .label (uint16), .bin (packed, input grid), occupancy bitmap; clears `best`.
 cudaError_t vx_launch_emit(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, cudaStream_t stream);
 
-// K4: occlusion pass + invalid passes, one CTA per frame.
+// K4: occlusion pass + invalid passes, one CTA per frame; every CTA claims one of the n_scratch scratch
+// buffers (locks[i]: 0 free / 1 taken) -- n_scratch must be >= vx_visibility_resident_ctas().
 cudaError_t vx_visibility_prepare();  // opt-in to large dynamic shared memory (once per process)
+int vx_visibility_resident_ctas(int device);  // CTAs of the kernel the device holds at once
 cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, uint32_t n_slots,
-                                 const float* endpoints, VxGridGeom geom, cudaStream_t stream);
+                                 const float* endpoints, VxGridGeom geom, const VxVisScratch* scratch, uint32_t n_scratch,
+                                 uint32_t* locks, cudaStream_t stream);
 uint64_t vx_visibility_visits(VxGridGeom geom);  // visits per pass (must stay < 2^25)
 
 // K5b: occl / alive bitmaps -> MSB-first packed .occluded / .invalid.

@@ -41,8 +41,8 @@ namespace {
 
 constexpr int kVisThreads = 128;
 constexpr int kVisWarps = kVisThreads / 32;
-constexpr int kMaxLive = 2048;    // live cells per wave
-constexpr int kMaxChunks = 512;   // chunk = <= 32 consecutive z of one column
+constexpr int kMaxLive = 1536;    // live cells per wave
+constexpr int kMaxChunks = 256;   // chunk = <= 32 consecutive z of one column
 constexpr int kChunksPerThread = kMaxChunks / kVisThreads;
 constexpr int kLivePerThread = kMaxLive / kVisThreads;
 constexpr uint32_t kSet = 0x80000000u;
@@ -69,6 +69,7 @@ struct VisShared {
   uint32_t any_edge;
   uint32_t undecided;
   uint32_t queue;
+  uint32_t scratch_id;
 };
 
 struct Wave {
@@ -205,8 +206,7 @@ __device__ __forceinline__ void prefix_walk(const Frame& f, const Wave& w, const
   const int32_t normal = w.face == 0 ? 0 : 1;
   for (;;) {
     if (r.next_axis() == normal) return;
-    if (!r.advance()) return;
-    if (!r.inside(f.g)) return;
+    if (!r.advance()) return;  // a ray that advances stays inside the grid (it breaks on the boundary layer)
     if (occupied(f, sm, r.i, r.j, r.k)) return;
     const int32_t x = live_rank(f, w, sm, r.i, r.j, r.k);
     if (x > (int32_t)rc) fn((uint32_t)x);
@@ -219,7 +219,8 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
   const uint32_t lane = threadIdx.x & 31u;
   const int32_t normal = w.face == 0 ? 0 : 1;
   bool active = false, exhausted = false, pending = false, in_face = false;
-  uint32_t pend_word = 0, rc = 0, id = 0, len = 0;
+  uint32_t pend_word = 0, rc = 0, id = 0, len = 0, L = 0;
+  const int32_t stride_j = f.g.nz, stride_i = f.g.ny * f.g.nz;
   VxRay r;
   for (;;) {
     const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
@@ -236,6 +237,7 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
           int32_t i, j, k;
           wave_cell(f, w, sm.rcell[rc], i, j, k);
           r.begin(f.g, i, j, k, f.e0, f.e1, f.e2);
+          L = lin(f.g, i, j, k);
           active = true;
           pending = false;
           in_face = true;
@@ -259,20 +261,21 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
           free_cell = false;
         }
       } else if (len > 0 && coarse_set(f, sm, r.i, r.j, r.k)) {
-        const uint32_t L = lin(f.g, r.i, r.j, r.k);
         pend_word = __ldg(f.occ + (L >> 5)) >> (L & 31u);  // consumed in the next iteration
         pending = true;
         free_cell = false;
       }
       if (free_cell) {
-        atomicMax(&f.memo[lin(f.g, r.i, r.j, r.k)], (f.epoch << kEpochShift) | id);
+        atomicMax(&f.memo[L], (f.epoch << kEpochShift) | id);
+        const int32_t axis = r.next_axis();
         if (in_face) {
           const int32_t x = live_rank(f, w, sm, r.i, r.j, r.k);
           if (x >= (int32_t)rc) atomicMax(&sm.owner[x], kSet | id);
-          if (r.next_axis() == normal) in_face = false;
+          if (axis == normal) in_face = false;
         }
         ++len;
-        if (!r.advance() || !r.inside(f.g)) finished = true;
+        L += (uint32_t)(axis == 0 ? r.sx * stride_i : (axis == 1 ? r.sy * stride_j : r.sz));
+        if (!r.advance()) finished = true;  // a ray that advances stays inside the grid
       }
       if (finished) {
         if (hit) atomicOr(&f.hitbits[id >> 5], 1u << (id & 31u));
@@ -526,9 +529,12 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   return w.ncols;
 }
 
-__global__ void __launch_bounds__(kVisThreads, 6)
+constexpr int kVisCtasPerSm = 7;  // 7 x (30 KB + 1 KB) of shared memory, 7 x 128 x 72 registers
+
+__global__ void __launch_bounds__(kVisThreads, kVisCtasPerSm)
 vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restrict__ frames,
-                     const float* __restrict__ endpoints, const VxGridGeom g, const uint32_t hit_words) {
+                     const float* __restrict__ endpoints, const VxGridGeom g, const uint32_t hit_words,
+                     const VxVisScratch* __restrict__ scratch, const uint32_t n_scratch, uint32_t* locks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VisShared& sm = *reinterpret_cast<VisShared*>(smem_raw);
   const VxSlot& slot = slots[blockIdx.x];
@@ -537,13 +543,23 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
   const uint32_t nvox = (uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz;
   const uint32_t words = (nvox + 31u) >> 5;
 
+  // claim a scratch buffer: at most as many CTAs are resident as there are buffers, so one is free
+  if (tid == 0) {
+    uint32_t s = blockIdx.x % n_scratch;
+    while (atomicCAS(&locks[s], 0u, 1u) != 0u) s = s + 1u == n_scratch ? 0u : s + 1u;
+    __threadfence();
+    sm.scratch_id = s;
+  }
+  __syncthreads();
+  const uint32_t scratch_id = sm.scratch_id;
+
   Frame f;
   f.g = g;
   f.cpc = (g.nz + 31) >> 5;
   f.occ = slot.occ;
   f.live = slot.alive;
-  f.memo = slot.memo;
-  f.hitbits = slot.hitbits;
+  f.memo = scratch[scratch_id].memo;
+  f.hitbits = scratch[scratch_id].hitbits;
   f.occl = slot.occl;
   f.cshift = -1;
   f.cyb = 0;
@@ -635,7 +651,10 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     atomicAdd(&slot.counters[0], rays);
     atomicAdd(&slot.counters[1], steps);
   }
+  __syncthreads();
   if (tid == 0) {
+    __threadfence();
+    atomicExch(&locks[scratch_id], 0u);  // release the scratch buffer
     slot.counters[2] = st.waves;
     slot.counters[3] = st.resolve_waves;
     slot.counters[4] = st.rounds;
@@ -649,11 +668,20 @@ cudaError_t vx_visibility_prepare() {
   return cudaFuncSetAttribute(vx_visibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisShared));
 }
 
+int vx_visibility_resident_ctas(int device) {
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vx_visibility_kernel, kVisThreads, sizeof(VisShared)) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+  return per_sm * sms;
+}
+
 cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, uint32_t n_slots,
-                                 const float* endpoints, VxGridGeom geom, cudaStream_t stream) {
+                                 const float* endpoints, VxGridGeom geom, const VxVisScratch* scratch, uint32_t n_scratch,
+                                 uint32_t* locks, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
   const uint32_t hit_words = (uint32_t)(vx_visibility_visits(geom) / 32u + 1u);
-  vx_visibility_kernel<<<n_slots, kVisThreads, sizeof(VisShared), stream>>>(slots, frames, endpoints, geom, hit_words);
+  vx_visibility_kernel<<<n_slots, kVisThreads, sizeof(VisShared), stream>>>(slots, frames, endpoints, geom, hit_words, scratch,
+                                                                           n_scratch, locks);
   return cudaGetLastError();
 }
 

@@ -178,7 +178,12 @@ int runGenData(const Config& config, const std::string& sequenceDir, const std::
     std::cout << "[voxelizer_b200] " << gi.resolution << "; num. voxels = [" << gi.size[0] << ", " << gi.size[1] << ", " << gi.size[2]
               << "], " << targets.size() << " target scans, batches of " << vx_frames_in_flight(ctx) << std::endl;
 
-  const uint32_t batch = std::max<uint32_t>(1, vx_frames_in_flight(ctx));
+  // equal batches: a short last batch would leave most of the device idle for a whole batch time
+  uint32_t batch = std::max<uint32_t>(1, vx_frames_in_flight(ctx));
+  if (!targets.empty()) {
+    const size_t n_batches = (targets.size() + batch - 1) / batch;
+    batch = uint32_t((targets.size() + n_batches - 1) / n_batches);
+  }
   OutputRing rings[2];
   std::vector<std::thread> writers;
   std::atomic<bool> writeFailed(false);
