@@ -499,6 +499,12 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
     c->own_stream = true;
   }
   for (int i = 0; i < EV_COUNT; ++i) VX_CREATE_CUDA(cudaEventCreate(&c->ev[i]));
+  {  // scans live in the device's stream-ordered memory pool; keep freed blocks for the next upload
+    cudaMemPool_t pool;
+    VX_CREATE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    VX_CREATE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   VX_CREATE_CUDA(vx_visibility_prepare());
 
   derive_geometry(*grid, c->geom);
@@ -584,9 +590,10 @@ void vx_destroy(vx_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_slots(c);
   for (auto& kv : c->scans) {
-    cudaFree(kv.second.points);
-    cudaFree(kv.second.labels);
+    if (kv.second.points) cudaFreeAsync(kv.second.points, c->stream);
+    if (kv.second.labels) cudaFreeAsync(kv.second.labels, c->stream);
   }
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (ScratchMem& m : c->scratch)
     if (m.arena) cudaFree(m.arena);
   if (c->d_scratch) cudaFree(c->d_scratch);
@@ -628,11 +635,11 @@ int vx_upload_scan(vx_ctx* c, uint32_t scan_id, const float* xyzr, const uint32_
   DeviceScan s;
   s.n = n;
   if (n) {
-    VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&s.points), (size_t)n * sizeof(float4)));
-    VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&s.labels), (size_t)n * sizeof(uint32_t)));
+    // stream-ordered pool allocation: no device-wide synchronisation per scan
+    VX_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&s.points), (size_t)n * sizeof(float4), c->stream));
+    VX_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&s.labels), (size_t)n * sizeof(uint32_t), c->stream));
     VX_CUDA(c, cudaMemcpyAsync(s.points, xyzr, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     VX_CUDA(c, cudaMemcpyAsync(s.labels, labels, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    VX_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   c->scans[scan_id] = s;
   return VX_OK;
@@ -642,8 +649,8 @@ int vx_evict_scan(vx_ctx* c, uint32_t scan_id) {
   if (!c) return VX_ERR_INVALID;
   const auto it = c->scans.find(scan_id);
   if (it == c->scans.end()) return VX_OK;
-  cudaFree(it->second.points);
-  cudaFree(it->second.labels);
+  if (it->second.points) cudaFreeAsync(it->second.points, c->stream);
+  if (it->second.labels) cudaFreeAsync(it->second.labels, c->stream);
   c->scans.erase(it);
   return VX_OK;
 }
@@ -651,8 +658,8 @@ int vx_evict_scan(vx_ctx* c, uint32_t scan_id) {
 int vx_evict_all(vx_ctx* c) {
   if (!c) return VX_ERR_INVALID;
   for (auto& kv : c->scans) {
-    cudaFree(kv.second.points);
-    cudaFree(kv.second.labels);
+    if (kv.second.points) cudaFreeAsync(kv.second.points, c->stream);
+    if (kv.second.labels) cudaFreeAsync(kv.second.labels, c->stream);
   }
   c->scans.clear();
   return VX_OK;

@@ -51,6 +51,7 @@ constexpr uint32_t kIdMask = (1u << kEpochShift) - 1u;
 constexpr uint32_t kMaxEpoch = 127;       // epochs 1..127 (0 = never written)
 constexpr uint32_t kCoarseWords = 4096;   // 131072 block bits
 constexpr uint32_t kRefillLanes = 8;      // idle lanes that trigger a refill of the tracer warp
+constexpr uint32_t kRaysPerTracer = 32;   // casters per tracing warp (more warps = shorter critical path)
 
 struct VisShared {
   uint32_t coarse[kCoarseWords];    // bit per (2^s x 2^s x 1) block: any voxel occupied
@@ -95,6 +96,7 @@ struct Frame {
   uint32_t* hitbits; // [visits / 32 + 1] ray id -> ended on an occupied cell (this pass)
   uint32_t* occl;
   float e0, e1, e2;
+  int32_t ex, ey, ez;  // end voxel of the pass (VoxelGrid.h:99-102: truncation)
   uint32_t epoch;
   bool inv;
 };
@@ -214,68 +216,97 @@ __device__ __forceinline__ void prefix_walk(const Frame& f, const Wave& w, const
 }
 
 // Phase C: the lanes of the calling warp pull casters from sm.queue and walk the reference's
-// occludedBy() once per ray.
+// occludedBy() once per ray.  The loop body is the unit of work of the whole path, so the ray lives in
+// scalars: the same operations in the same order as VxRay (vx_dda.h), with the linear index kept
+// incrementally and the boundary tests of VoxelGrid.cpp:286-287,307 folded into one unsigned compare.
 __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_t n_cast, uint32_t id_base, Stats& st) {
   const uint32_t lane = threadIdx.x & 31u;
   const int32_t normal = w.face == 0 ? 0 : 1;
-  bool active = false, exhausted = false, pending = false, in_face = false;
-  uint32_t pend_word = 0, rc = 0, id = 0, len = 0, L = 0;
+  const uint32_t enc_epoch = f.epoch << kEpochShift;
   const int32_t stride_j = f.g.nz, stride_i = f.g.ny * f.g.nz;
-  VxRay r;
+  bool active = false, exhausted = false, in_face = false, refill = true;
+  uint32_t rc = 0, id = 0, len = 0, L = 0;
+  int32_t i = 0, j = 0, k = 0, sx = 0, sy = 0, sz = 0;
+  float tx = 0.f, ty = 0.f, tz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
   for (;;) {
-    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
-    if (!exhausted && (idle == 0xFFFFFFFFu || (uint32_t)__popc(idle) >= kRefillLanes)) {
-      uint32_t base = 0;
-      if (lane == (uint32_t)(__ffs(idle) - 1)) base = atomicAdd(&sm.queue, (uint32_t)__popc(idle));
-      base = __shfl_sync(0xFFFFFFFFu, base, __ffs(idle) - 1);
-      if (base + (uint32_t)__popc(idle) >= n_cast) exhausted = true;
-      if (!active) {
-        const uint32_t s = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
-        if (s < n_cast) {
-          rc = sm.cand[s];
-          id = id_base + s;
-          int32_t i, j, k;
-          wave_cell(f, w, sm.rcell[rc], i, j, k);
-          r.begin(f.g, i, j, k, f.e0, f.e1, f.e2);
-          L = lin(f.g, i, j, k);
-          active = true;
-          pending = false;
-          in_face = true;
-          len = 0;
-          ++st.rays;
+    if (refill) {  // warp-uniform: some lane ended its ray in the previous iteration (or this is the first one)
+      const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+      if (!exhausted && (idle == 0xFFFFFFFFu || (uint32_t)__popc(idle) >= kRefillLanes)) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(idle) - 1)) base = atomicAdd(&sm.queue, (uint32_t)__popc(idle));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(idle) - 1);
+        if (base + (uint32_t)__popc(idle) >= n_cast) exhausted = true;
+        if (!active) {
+          const uint32_t s = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+          if (s < n_cast) {
+            rc = sm.cand[s];
+            id = id_base + s;
+            wave_cell(f, w, sm.rcell[rc], i, j, k);
+            const VxAxis ax = vx_axis_setup(f.g.off[0], f.g.res, f.g.nx, i, f.e0);
+            const VxAxis ay = vx_axis_setup(f.g.off[1], f.g.res, f.g.ny, j, f.e1);
+            const VxAxis az = vx_axis_setup(f.g.off[2], f.g.res, f.g.nz, k, f.e2);
+            tx = ax.tmax; dx = ax.tdelta; sx = ax.step;
+            ty = ay.tmax; dy = ay.tdelta; sy = ay.step;
+            tz = az.tmax; dz = az.tdelta; sz = az.step;
+            L = lin(f.g, i, j, k);
+            active = true;
+            in_face = true;
+            len = 0;
+            ++st.rays;
+          }
         }
       }
+      if (!__any_sync(0xFFFFFFFFu, active)) {
+        if (exhausted) break;
+        continue;
+      }
     }
-    if (!__any_sync(0xFFFFFFFFu, active)) {
-      if (exhausted) break;
-      continue;
-    }
+    bool finished = false;
     if (active) {
-      // cell (r.i, r.j, r.k) is inside the grid.  The caster's own cell is free (live cells are).
-      bool free_cell = true, finished = false, hit = false;
-      if (pending) {
-        pending = false;
-        if (pend_word & 1u) {
-          finished = true;
-          hit = true;
-          free_cell = false;
-        }
-      } else if (len > 0 && coarse_set(f, sm, r.i, r.j, r.k)) {
-        pend_word = __ldg(f.occ + (L >> 5)) >> (L & 31u);  // consumed in the next iteration
-        pending = true;
-        free_cell = false;
+      // (i,j,k) = the current cell: inside the grid and free.  Which axis steps next (VoxelGrid.cpp:299-301):
+      // {2,1,2,1,2,2,0,0}[(tx<ty)<<2 | (tx<tz)<<1 | (ty<tz)]
+      const bool lt01 = tx < ty, lt02 = tx < tz, lt12 = ty < tz;
+      const bool a0 = lt01 && lt02;
+      const bool a1 = !lt01 && lt12;
+      const uint32_t Lc = L;
+      bool hit = false;
+      if (in_face) {  // cells of this wave visited at or after the caster see this ray
+        const int32_t x = live_rank(f, w, sm, i, j, k);
+        if (x >= (int32_t)rc) atomicMax(&sm.owner[x], kSet | id);
+        if ((normal == 0 && a0) || (normal == 1 && a1)) in_face = false;
       }
-      if (free_cell) {
-        atomicMax(&f.memo[L], (f.epoch << kEpochShift) | id);
-        const int32_t axis = r.next_axis();
-        if (in_face) {
-          const int32_t x = live_rank(f, w, sm, r.i, r.j, r.k);
-          if (x >= (int32_t)rc) atomicMax(&sm.owner[x], kSet | id);
-          if (axis == normal) in_face = false;
-        }
-        ++len;
-        L += (uint32_t)(axis == 0 ? r.sx * stride_i : (axis == 1 ? r.sy * stride_j : r.sz));
-        if (!r.advance()) finished = true;  // a ray that advances stays inside the grid
+      // step (VoxelGrid.cpp:304-305)
+      int32_t pos, size;
+      if (a0) {
+        i += sx;
+        tx = VX_FADD(tx, dx);
+        L += (uint32_t)(sx * stride_i);
+        pos = i;
+        size = f.g.nx;
+      } else if (a1) {
+        j += sy;
+        ty = VX_FADD(ty, dy);
+        L += (uint32_t)(sy * stride_j);
+        pos = j;
+        size = f.g.ny;
+      } else {
+        k += sz;
+        tz = VX_FADD(tz, dz);
+        L += (uint32_t)sz;
+        pos = k;
+        size = f.g.nz;
+      }
+      // leaves the grid (pos == Out after a positive step, pos <= 0 after a negative one: Out = 0 there and a
+      // step to -1 ends at the top of the reference loop), or reaches the end voxel: the ray misses
+      finished = (uint32_t)(pos - 1) >= (uint32_t)(size - 1) || (i == f.ex && j == f.ey && k == f.ez);
+      uint32_t word = 0;
+      const bool test = !finished && coarse_set(f, sm, i, j, k);
+      if (test) word = __ldg(f.occ + (L >> 5));  // in flight while the current cell is recorded
+      atomicMax(&f.memo[Lc], enc_epoch | id);
+      ++len;
+      if (test && ((word >> (L & 31u)) & 1u)) {
+        finished = true;
+        hit = true;
       }
       if (finished) {
         if (hit) atomicOr(&f.hitbits[id >> 5], 1u << (id & 31u));
@@ -283,6 +314,7 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
         active = false;
       }
     }
+    refill = __any_sync(0xFFFFFFFFu, finished);
   }
 }
 
@@ -497,7 +529,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
     }
 
     // ---- C: trace
-    uint32_t tracers = (n_cast + 47u) / 48u;
+    uint32_t tracers = (n_cast + kRaysPerTracer - 1u) / kRaysPerTracer;
     if (tracers > (uint32_t)kVisWarps) tracers = kVisWarps;
     if ((tid >> 5) < tracers) trace_warp(f, w, sm, n_cast, id_base, st);
     __syncthreads();
@@ -615,6 +647,9 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
       f.e1 = e[1];
       f.e2 = e[2];
     }
+    f.ex = vx_trunc_i32(VX_FDIV(VX_FSUB(f.e0, g.off[0]), g.res));
+    f.ey = vx_trunc_i32(VX_FDIV(VX_FSUB(f.e1, g.off[1]), g.res));
+    f.ez = vx_trunc_i32(VX_FDIV(VX_FSUB(f.e2, g.off[2]), g.res));
     f.epoch = (pass % kMaxEpoch) + 1u;
     if (pass % kMaxEpoch == 0) {  // first pass, or the epoch counter restarts: forget every memo
       for (uint32_t x = tid; x < nvox; x += kVisThreads) f.memo[x] = 0u;
