@@ -32,7 +32,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(vx.Options) == 32
     assert C.sizeof(vx.FrameDesc) == 96
     assert C.sizeof(vx.GridInfo) == 56
-    assert C.sizeof(vx.StageTimes) == 22 * 8
+    assert C.sizeof(vx.StageTimes) == 26 * 8
 
 
 def test_no_cpu_fallback_without_device():

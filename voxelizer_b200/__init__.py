@@ -74,7 +74,7 @@ class StageTimes(C.Structure):
         ("pack_ms", C.c_double), ("total_ms", C.c_double), ("frames", C.c_uint64), ("points_read", C.c_uint64),
         ("fill_launches", C.c_uint64), ("vote_launches", C.c_uint64), ("emit_launches", C.c_uint64),
         ("visibility_launches", C.c_uint64), ("pack_launches", C.c_uint64), ("rays_cast", C.c_uint64), ("dda_steps", C.c_uint64),
-        ("vis_waves", C.c_uint64), ("vis_resolve_waves", C.c_uint64), ("vis_rounds", C.c_uint64), ("vis_cycles", C.c_uint64 * 4),
+        ("vis_waves", C.c_uint64), ("vis_resolve_waves", C.c_uint64), ("vis_rounds", C.c_uint64), ("vis_cycles", C.c_uint64 * 8),
     ]
 
     def as_dict(self):
@@ -175,6 +175,10 @@ def host_lib():
         L.vxh_gen_data.restype = C.c_int
         L.vxh_gen_data.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(GenDataStats)]
+        L.vxh_gen_data_facade.restype = C.c_int
+        L.vxh_gen_data_facade.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int64, C.POINTER(C.c_uint64)]
+        L.vxh_facade_probe.restype = C.c_int
+        L.vxh_facade_probe.argtypes = [C.c_int, C.c_float] + [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_uint32] + [C.c_void_p] * 8
         _host = L
     return _host
 
@@ -320,6 +324,42 @@ def gen_data(cfg_path: str, seq_dir: str, out_dir: str, device: int = 0, shard=(
 # ------------------------------------------------------------------------------------------------------
 # The CUDA backend through the C ABI
 # ------------------------------------------------------------------------------------------------------
+def gen_data_facade(cfg_path: str, seq_dir: str, out_dir: str, device: int = 0, max_frames: int = -1) -> int:
+    """gen_data written against the kept reference API (VoxelGrid / fillVoxelGrid / saveVoxelGrid facade,
+    host/gen_data_facade.cpp), one frame at a time.  Returns the number of frames written."""
+    H = host_lib()
+    os.makedirs(out_dir, exist_ok=True)
+    n = C.c_uint64(0)
+    if H.vxh_gen_data_facade(cfg_path.encode(), seq_dir.encode(), out_dir.encode(), device, max_frames, C.byref(n)) != 0:
+        raise VxError(H.vxh_last_error().decode())
+    return int(n.value)
+
+
+def facade_probe(resolution, min_extent, max_extent, points4, labels, endpoints, device: int = 0) -> dict:
+    """vxb::VoxelGrid used directly (raw insert, updateOcclusions, updateInvalid, every per-voxel query).
+    Arrays come back in the reference's internal index order i + j*Sx + k*Sx*Sy."""
+    H = host_lib()
+    pts = _f32(points4).reshape(-1, 4)
+    lab = _u32(labels)
+    ep = _f32(endpoints).reshape(-1, 3)
+    mn, mx = _f32(list(min_extent)[:3]), _f32(list(max_extent)[:3])
+    size = np.zeros(3, np.uint32)
+    off = np.zeros(3, np.float32)
+    # sizes first (needs the grid): probe once with no points to learn them
+    be = Backend(resolution, list(min_extent)[:3], list(max_extent)[:3], 0.0, float("inf"), hidecar=False, device=device, frames_in_flight=1)
+    nv = be.nvox
+    be.close()
+    out = {k: np.zeros(nv, np.uint8) for k in ("occluded", "free", "invalid")}
+    out.update({k: np.zeros(nv, np.uint32) for k in ("count", "n_labels", "majority")})
+    rc = H.vxh_facade_probe(device, C.c_float(resolution), _p(mn), _p(mx), _p(pts), _p(lab), len(lab), _p(ep), len(ep), _p(size), _p(off),
+                            _p(out["occluded"]), _p(out["free"]), _p(out["invalid"]), _p(out["count"]), _p(out["n_labels"]), _p(out["majority"]))
+    if rc != 0:
+        raise VxError(H.vxh_last_error().decode())
+    out["size"] = tuple(int(x) for x in size)
+    out["offset"] = off
+    return out
+
+
 @dataclass
 class FrameSpec:
     prior_ids: np.ndarray

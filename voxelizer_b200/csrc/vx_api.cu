@@ -439,7 +439,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   c->times.vis_waves += stats[2];
   c->times.vis_resolve_waves += stats[3];
   c->times.vis_rounds += stats[4];
-  for (int k = 0; k < 4; ++k) c->times.vis_cycles[k] += stats[5 + k];
+  for (int k = 0; k < 8; ++k) c->times.vis_cycles[k] += stats[5 + k];
   return VX_OK;
 }
 

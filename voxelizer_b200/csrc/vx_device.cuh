@@ -15,7 +15,7 @@
 
 #define VX_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define VX_MAX_PROBES 4096u
-#define VX_SLOT_STATS 9
+#define VX_SLOT_STATS 13
 
 // Open-addressing histogram of one grid of one frame: (L << 16 | label16) -> count.
 struct VxTable {
@@ -41,7 +41,7 @@ struct VxSlot {
   uint32_t* out_bin;          // [words] MSB-first packed
   uint32_t* out_occluded;     // [words]
   uint32_t* out_invalid;      // [words]
-  unsigned long long* counters;  // [VX_SLOT_STATS] rays, steps, waves, resolve waves, rounds, cycles[4]
+  unsigned long long* counters;  // [VX_SLOT_STATS] rays, steps, waves, resolve waves, rounds, cycles[8]
 };
 
 // Scratch of one RESIDENT visibility CTA (claimed at run time, so the pool is as large as the number
