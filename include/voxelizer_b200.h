@@ -65,12 +65,13 @@ typedef struct vx_filter_desc {
 typedef struct vx_options {
   uint32_t frames_in_flight;     /* frames per internal batch = one visibility launch, one CTA per frame
                                     (default: 4 x the CTAs the device holds at once, memory permitting) */
-  uint32_t table_log2_capacity;  /* initial (voxel,label) histogram slots per frame, log2 (default 21) */
+  uint32_t table_log2_capacity;  /* initial (voxel,label) histogram slots per frame, log2 (default 18; grown x4
+                                    and the batch redone when a frame overflows it) */
   void* stream;                  /* cudaStream_t to run on (e.g. the caller's framework stream so that its
                                     events bracket the work); NULL = a private non-blocking stream */
   uint32_t debug;                /* 1: keep histogram tables after a batch for vx_debug_dump */
   uint32_t table_sets;           /* frames per fill -> vote -> emit launch; frames this far apart share one set of
-                                    histogram tables (default 32) */
+                                    histogram tables (default 128) */
   uint32_t reserved[2];
 } vx_options;
 

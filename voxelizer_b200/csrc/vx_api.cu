@@ -4,6 +4,7 @@
 // CUDA is unusable every entry point reports VX_ERR_NO_DEVICE / VX_ERR_CUDA.
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -23,12 +24,10 @@ struct DeviceScan {
   uint32_t n = 0;
 };
 
-// Histogram tables + vote arrays: shared by the frames of a batch that are `table_sets` apart.
+// Histogram + winner tables: shared by the frames of a batch that are `table_sets` apart.
 struct TableSet {
   void* arena = nullptr;
   VxTable input{}, target{};
-  unsigned long long* best_input = nullptr;
-  unsigned long long* best_target = nullptr;
 };
 
 // Per-frame state that outlives fill -> vote -> emit: bitmaps and the four output images.
@@ -66,7 +65,7 @@ struct vx_ctx {
 
   uint32_t max_slots = 0;   // frames per batch (one visibility launch)
   uint32_t table_sets = 0;  // frames per fill -> vote -> emit launch
-  uint32_t log2_target = 21, log2_input = 18;
+  uint32_t log2_target = 18, log2_input = 15;
   bool keep_tables = false;
   bool tables_dirty = false;  // tables hold the previous batch (debug mode)
   uint32_t dirty_slots = 0;
@@ -129,12 +128,10 @@ void derive_geometry(const vx_grid_desc& d, VxGridGeom& g) {
 
 size_t table_bytes(uint32_t log2_cap) {
   const size_t cap = (size_t)1 << log2_cap;
-  return align_up(cap * 8, 256) + align_up(cap * 4, 256) + align_up(cap * 4, 256);
+  return align_up(cap * 8, 256) + align_up(cap * 4, 256) + align_up(cap / 2 * 4, 256) + align_up(cap / 2 * 8, 256);
 }
 
-size_t table_set_bytes(const vx_ctx* c) {
-  return table_bytes(c->log2_target) + table_bytes(c->log2_input) + 2 * align_up(c->nvox * 8, 256);
-}
+size_t table_set_bytes(const vx_ctx* c) { return table_bytes(c->log2_target) + table_bytes(c->log2_input); }
 
 size_t frame_bytes(const vx_ctx* c) { return 6 * align_up((size_t)c->words * 4, 256) + align_up(c->nvox * 2, 256); }
 
@@ -150,26 +147,20 @@ struct Carver {
 };
 
 int alloc_table_set(vx_ctx* c, TableSet& t) {
-  VX_CUDA(c, cudaMalloc(&t.arena, table_set_bytes(c)));
+  const size_t bytes = table_set_bytes(c);
+  VX_CUDA(c, cudaMalloc(&t.arena, bytes));
   Carver cv{static_cast<unsigned char*>(t.arena)};
   auto carve = [&](VxTable& tb, uint32_t log2_cap) {
     const size_t cap = (size_t)1 << log2_cap;
     tb.keys = reinterpret_cast<unsigned long long*>(cv.take(cap * 8));
     tb.counts = reinterpret_cast<uint32_t*>(cv.take(cap * 4));
-    tb.used = reinterpret_cast<uint32_t*>(cv.take(cap * 4));
+    tb.vkeys = reinterpret_cast<uint32_t*>(cv.take(cap / 2 * 4));
+    tb.vbest = reinterpret_cast<unsigned long long*>(cv.take(cap / 2 * 8));
     tb.log2_cap = log2_cap;
-    return cap;
   };
-  const size_t cap_t = carve(t.target, c->log2_target), cap_i = carve(t.input, c->log2_input);
-  t.best_input = reinterpret_cast<unsigned long long*>(cv.take(c->nvox * 8));
-  t.best_target = reinterpret_cast<unsigned long long*>(cv.take(c->nvox * 8));
-  // empty tables, empty vote arrays (vote / emit leave them empty again)
-  VX_CUDA(c, cudaMemsetAsync(t.target.keys, 0xFF, cap_t * 8, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(t.target.counts, 0, cap_t * 4, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(t.input.keys, 0xFF, cap_i * 8, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(t.input.counts, 0, cap_i * 4, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(t.best_input, 0, c->nvox * 8, c->stream));
-  VX_CUDA(c, cudaMemsetAsync(t.best_target, 0, c->nvox * 8, c->stream));
+  carve(t.target, c->log2_target);
+  carve(t.input, c->log2_input);
+  VX_CUDA(c, cudaMemsetAsync(t.arena, 0, bytes, c->stream));  // all-zero = empty (vote / emit leave them empty again)
   return VX_OK;
 }
 
@@ -180,14 +171,10 @@ int alloc_frame(vx_ctx* c, uint32_t index) {
   const TableSet& t = c->tables[index % c->table_sets];
   uint32_t* cnt = c->d_counters + (size_t)index * kCounterWords;
   s.dev.target = t.target;
-  s.dev.target.used_count = cnt + 0;
   s.dev.target.overflow = cnt + 1;
   s.dev.input = t.input;
-  s.dev.input.used_count = cnt + 2;
   s.dev.input.overflow = cnt + 3;
   s.dev.counters = reinterpret_cast<unsigned long long*>(cnt + 4);
-  s.dev.best_input = t.best_input;
-  s.dev.best_target = t.best_target;
   s.dev.occ = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
   s.dev.occl = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
   s.dev.alive = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
@@ -291,53 +278,74 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     n_ap += frames[f].n_prior + frames[f].n_past;
     n_ep += frames[f].n_endpoints;
   }
-  const size_t off_items = 0;
-  const size_t off_ap = align_up(off_items + n_items * sizeof(VxFillItem), 256);
+  const size_t off_works = 0;
+  const size_t off_uses = align_up(off_works + n_items * sizeof(VxScanWork), 256);
+  const size_t off_ap = align_up(off_uses + n_items * sizeof(VxScanUse), 256);
   const size_t off_ep = align_up(off_ap + n_ap * 16 * sizeof(float), 256);
   const size_t off_vis = align_up(off_ep + n_ep * 3 * sizeof(float), 256);
   const size_t total = align_up(off_vis + nb * sizeof(VxVisFrame), 256);
   rc = ensure_stage(c, total);
   if (rc != VX_OK) return rc;
-  VxFillItem* items = reinterpret_cast<VxFillItem*>(c->h_stage + off_items);
+  VxScanWork* works = reinterpret_cast<VxScanWork*>(c->h_stage + off_works);
+  VxScanUse* uses = reinterpret_cast<VxScanUse*>(c->h_stage + off_uses);
   float* ap = reinterpret_cast<float*>(c->h_stage + off_ap);
   float* ep = reinterpret_cast<float*>(c->h_stage + off_ep);
   VxVisFrame* vis = reinterpret_cast<VxVisFrame*>(c->h_stage + off_vis);
 
-  size_t ii = 0, ai = 0, ei = 0;
+  // Fill work per group of `table_sets` frames, organised by scan: every scan a group touches becomes one
+  // VxScanWork with the list of (frame, matrix, both) it goes into.
+  struct Use {
+    uint32_t scan_id, slot, ap_index, both;
+  };
+  const uint32_t n_sub = (nb + c->table_sets - 1) / c->table_sets;
+  std::vector<size_t> work_begin(n_sub + 1, 0);
+  std::vector<uint32_t> sub_max_points(n_sub, 0);
+  size_t wi = 0, ui = 0, ai = 0, ei = 0;
   uint64_t points = 0;
-  std::vector<size_t> item_begin(nb + 1, 0);
-  std::vector<uint32_t> frame_max_points(nb, 0);
-  for (uint32_t f = 0; f < nb; ++f) {
-    const vx_frame_desc& fr = frames[f];
-    item_begin[f] = ii;
-    if ((fr.n_prior && (!fr.prior_ids || !fr.ap_prior)) || (fr.n_past && (!fr.past_ids || !fr.ap_past)) || (fr.n_endpoints && !fr.endpoints))
-      return fail(c, VX_ERR_INVALID, "frame descriptor has null arrays");
-    for (int part = 0; part < 2; ++part) {
-      const uint32_t n = part == 0 ? fr.n_prior : fr.n_past;
-      const uint32_t* ids = part == 0 ? fr.prior_ids : fr.past_ids;
-      const float* aps = part == 0 ? fr.ap_prior : fr.ap_past;
-      for (uint32_t s = 0; s < n; ++s) {
-        const auto it = c->scans.find(ids[s]);
-        if (it == c->scans.end()) return fail(c, VX_ERR_UNKNOWN_SCAN, "scan " + std::to_string(ids[s]) + " is not resident");
-        VxFillItem& item = items[ii++];
-        item.points = it->second.points;
-        item.labels = it->second.labels;
-        item.n = it->second.n;
-        item.slot = f;
-        item.ap_index = (uint32_t)ai;
-        item.both = part == 0 ? 1u : 0u;
-        std::memcpy(ap + 16 * ai, aps + 16 * (size_t)s, 16 * sizeof(float));
-        ++ai;
-        if (item.n > frame_max_points[f]) frame_max_points[f] = item.n;
-        points += item.n;
+  std::vector<Use> group;
+  for (uint32_t gi = 0; gi < n_sub; ++gi) {
+    const uint32_t f0 = gi * c->table_sets, f1 = f0 + c->table_sets < nb ? f0 + c->table_sets : nb;
+    group.clear();
+    for (uint32_t f = f0; f < f1; ++f) {
+      const vx_frame_desc& fr = frames[f];
+      if ((fr.n_prior && (!fr.prior_ids || !fr.ap_prior)) || (fr.n_past && (!fr.past_ids || !fr.ap_past)) || (fr.n_endpoints && !fr.endpoints))
+        return fail(c, VX_ERR_INVALID, "frame descriptor has null arrays");
+      for (int part = 0; part < 2; ++part) {
+        const uint32_t n = part == 0 ? fr.n_prior : fr.n_past;
+        const uint32_t* ids = part == 0 ? fr.prior_ids : fr.past_ids;
+        const float* aps = part == 0 ? fr.ap_prior : fr.ap_past;
+        for (uint32_t s = 0; s < n; ++s) {
+          std::memcpy(ap + 16 * ai, aps + 16 * (size_t)s, 16 * sizeof(float));
+          group.push_back(Use{ids[s], f, (uint32_t)ai, part == 0 ? 1u : 0u});
+          ++ai;
+        }
       }
+      vis[f].n_endpoints = fr.n_endpoints;
+      vis[f].endpoint_offset = (uint32_t)ei;
+      if (fr.n_endpoints) std::memcpy(ep + 3 * ei, fr.endpoints, (size_t)fr.n_endpoints * 3 * sizeof(float));
+      ei += fr.n_endpoints;
     }
-    vis[f].n_endpoints = fr.n_endpoints;
-    vis[f].endpoint_offset = (uint32_t)ei;
-    if (fr.n_endpoints) std::memcpy(ep + 3 * ei, fr.endpoints, (size_t)fr.n_endpoints * 3 * sizeof(float));
-    ei += fr.n_endpoints;
+    std::stable_sort(group.begin(), group.end(), [](const Use& a, const Use& b) { return a.scan_id < b.scan_id; });
+    work_begin[gi] = wi;
+    for (size_t k = 0; k < group.size();) {
+      size_t k1 = k;
+      while (k1 < group.size() && group[k1].scan_id == group[k].scan_id) ++k1;
+      const auto it = c->scans.find(group[k].scan_id);
+      if (it == c->scans.end()) return fail(c, VX_ERR_UNKNOWN_SCAN, "scan " + std::to_string(group[k].scan_id) + " is not resident");
+      VxScanWork& w = works[wi++];
+      w.points = it->second.points;
+      w.labels = it->second.labels;
+      w.n = it->second.n;
+      w.use_begin = (uint32_t)ui;
+      w.use_count = (uint32_t)(k1 - k);
+      w.pad = 0;
+      for (size_t q = k; q < k1; ++q) uses[ui++] = VxScanUse{group[q].slot, group[q].ap_index, group[q].both};
+      if (w.n > sub_max_points[gi]) sub_max_points[gi] = w.n;
+      points += (uint64_t)w.n * (k1 - k);
+      k = k1;
+    }
   }
-  item_begin[nb] = ii;
+  work_begin[n_sub] = wi;
 
   cudaStream_t st = c->stream;
   if (c->tables_dirty) {  // debug mode kept the previous batch's tables
@@ -347,13 +355,13 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   VX_CUDA(c, cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, st));
   VX_CUDA(c, cudaMemsetAsync(c->d_counters, 0, (size_t)nb * kCounterWords * sizeof(uint32_t), st));
 
-  const VxFillItem* d_items = reinterpret_cast<const VxFillItem*>(c->d_stage + off_items);
+  const VxScanWork* d_works = reinterpret_cast<const VxScanWork*>(c->d_stage + off_works);
+  const VxScanUse* d_uses = reinterpret_cast<const VxScanUse*>(c->d_stage + off_uses);
   const float* d_ap = reinterpret_cast<const float*>(c->d_stage + off_ap);
   const float* d_ep = reinterpret_cast<const float*>(c->d_stage + off_ep);
   const VxVisFrame* d_vis = reinterpret_cast<const VxVisFrame*>(c->d_stage + off_vis);
 
   // fill -> vote -> emit in groups of `table_sets` frames (frames of different groups share tables)
-  const uint32_t n_sub = (nb + c->table_sets - 1) / c->table_sets;
   while (c->ev_sub.size() < (size_t)n_sub * 4) {
     cudaEvent_t e;
     VX_CUDA(c, cudaEventCreate(&e));
@@ -363,17 +371,15 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   VX_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], st));
   for (uint32_t g = 0; g < n_sub; ++g) {
     const uint32_t f0 = g * c->table_sets, f1 = f0 + c->table_sets < nb ? f0 + c->table_sets : nb;
-    uint32_t max_points = 0;
-    for (uint32_t f = f0; f < f1; ++f) max_points = frame_max_points[f] > max_points ? frame_max_points[f] : max_points;
-    const uint32_t n_sub_items = (uint32_t)(item_begin[f1] - item_begin[f0]);
+    const uint32_t n_works = (uint32_t)(work_begin[g + 1] - work_begin[g]);
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 0], st));
-    VX_CUDA(c, vx_launch_fill(d_items + item_begin[f0], n_sub_items, max_points, d_ap, c->d_slots, c->geom, c->filter, st));
+    VX_CUDA(c, vx_launch_fill(d_works + work_begin[g], n_works, sub_max_points[g], d_uses, d_ap, c->d_slots, c->geom, c->filter, st));
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 1], st));
-    VX_CUDA(c, vx_launch_vote(c->d_slots + f0, f1 - f0, c->keep_tables ? 1 : 0, st));
+    VX_CUDA(c, vx_launch_vote(c->d_slots + f0, f1 - f0, c->nvox, c->keep_tables ? 1 : 0, st));
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 2], st));
-    VX_CUDA(c, vx_launch_emit(c->d_slots + f0, f1 - f0, c->nvox, st));
+    VX_CUDA(c, vx_launch_emit(c->d_slots + f0, f1 - f0, st));
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 3], st));
-    fill_launches += (n_sub_items + 65534) / 65535;
+    fill_launches += (n_works + 65534) / 65535;
   }
   VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS_BEGIN], st));
   VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, c->d_scratch, (uint32_t)c->scratch.size(), c->d_locks, st));
@@ -430,7 +436,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   c->times.frames += nb;
   c->times.points_read += points;
   c->times.fill_launches += fill_launches;
-  c->times.vote_launches += n_sub;
+  c->times.vote_launches += 2 * n_sub;  // clear + vote
   c->times.emit_launches += n_sub;
   c->times.visibility_launches += 1;
   c->times.pack_launches += 1;
@@ -559,7 +565,7 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
     c->error = "the visibility kernel does not fit on this device";
     return bail(VX_ERR_CUDA);
   }
-  c->table_sets = options && options->table_sets ? options->table_sets : 32u;
+  c->table_sets = options && options->table_sets ? options->table_sets : 128u;
   size_t free_b = 0, total_b = 0;
   VX_CREATE_CUDA(cudaMemGetInfo(&free_b, &total_b));
   uint32_t want = options && options->frames_in_flight ? options->frames_in_flight : 4u * resident;
@@ -720,24 +726,24 @@ int vx_debug_dump(vx_ctx* c, uint32_t frame_index, int kind, void* dst, uint64_t
   if (kind == VX_DUMP_HIST_TARGET || kind == VX_DUMP_HIST_INPUT) {
     if (!c->keep_tables || !c->tables_dirty) return fail(c, VX_ERR_INVALID, "histogram dump needs vx_options.debug = 1");
     const VxTable& t = kind == VX_DUMP_HIST_TARGET ? s.target : s.input;
-    uint32_t used = 0;
-    VX_CUDA(c, cudaMemcpy(&used, t.used_count, 4, cudaMemcpyDeviceToHost));
-    *count = used;
-    if (!dst || used == 0) return VX_OK;
     const size_t cap = (size_t)1 << t.log2_cap;
-    std::vector<uint32_t> idx(used);
     std::vector<unsigned long long> keys(cap);
     std::vector<uint32_t> counts(cap);
-    VX_CUDA(c, cudaMemcpy(idx.data(), t.used, (size_t)used * 4, cudaMemcpyDeviceToHost));
     VX_CUDA(c, cudaMemcpy(keys.data(), t.keys, cap * 8, cudaMemcpyDeviceToHost));
     VX_CUDA(c, cudaMemcpy(counts.data(), t.counts, cap * 4, cudaMemcpyDeviceToHost));
+    uint64_t used = 0;
     uint32_t* o = static_cast<uint32_t*>(dst);
-    for (uint32_t u = 0; u < used; ++u) {
-      const unsigned long long k = keys[idx[u]];
-      o[3 * (size_t)u + 0] = (uint32_t)(k >> 16);
-      o[3 * (size_t)u + 1] = (uint32_t)(k & 0xFFFFull);
-      o[3 * (size_t)u + 2] = counts[idx[u]];
+    for (size_t h = 0; h < cap; ++h) {
+      if (keys[h] == 0ull) continue;
+      if (o) {
+        const unsigned long long k = keys[h] - 1ull;
+        o[3 * used + 0] = (uint32_t)(k >> 16);
+        o[3 * used + 1] = (uint32_t)(k & 0xFFFFull);
+        o[3 * used + 2] = counts[h];
+      }
+      ++used;
     }
+    *count = used;
     return VX_OK;
   }
   if (kind == VX_DUMP_OCCUPANCY || kind == VX_DUMP_OCCLUDED || kind == VX_DUMP_INVALID) {

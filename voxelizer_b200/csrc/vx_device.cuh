@@ -13,27 +13,26 @@
 
 #include "vx_dda.h"
 
-#define VX_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define VX_MAX_PROBES 4096u
 #define VX_SLOT_STATS 13
 
-// Open-addressing histogram of one grid of one frame: (L << 16 | label16) -> count.
+// Open-addressing histogram of one grid of one frame: (L << 16 | label16) -> count, and the per-voxel
+// winner table the vote builds from it: L -> max(count << 16 | 0xFFFF - label).  Keys are stored + 1 so
+// that an all-zero table is empty.
 struct VxTable {
-  unsigned long long* keys;  // [cap], VX_EMPTY_KEY when free
-  uint32_t* counts;          // [cap]
-  uint32_t* used;            // [cap] slots claimed this frame (for O(used) vote + reset)
-  uint32_t* used_count;      // [1]
-  uint32_t* overflow;        // [1] set when a probe sequence ran out
+  unsigned long long* keys;   // [cap]   ((L << 16 | label) + 1), 0 = free
+  uint32_t* counts;           // [cap]
+  uint32_t* vkeys;            // [cap/2] (L + 1), 0 = free
+  unsigned long long* vbest;  // [cap/2]
+  uint32_t* overflow;         // [1] set when a probe sequence ran out (either table)
   uint32_t log2_cap;
 };
 
-// One frame of a batch.  The histogram tables / vote arrays are shared by frames that are `table_sets`
-// apart (they are processed by different fill -> vote -> emit launches); the rest is per frame.
+// One frame of a batch.  The histogram tables are shared by frames that are `table_sets` apart (they are
+// processed by different fill -> vote -> emit launches); the rest is per frame.
 struct VxSlot {
   VxTable input;              // priorGrid histogram
   VxTable target;             // pastGrid histogram
-  unsigned long long* best_input;   // [nvox] count << 16 | (0xFFFF - label), 0 = empty voxel
-  unsigned long long* best_target;  // [nvox]
   uint32_t* occ;              // [words] target grid occupancy (count > 0), bit L
   uint32_t* occl;             // [words] occlusions_ > -1
   uint32_t* alive;            // [words] free cells with invalid_ != -1 (the traversal's live set)
@@ -51,12 +50,19 @@ struct VxVisScratch {
   uint32_t* hitbits;  // [visits / 32 + 1] ray id -> the ray ended on an occupied cell (current pass)
 };
 
-// One (frame, scan) unit of fill work.
-struct VxFillItem {
+// Fill work is organised by SCAN: a tile of a scan is loaded once and inserted into every frame of the
+// launch whose window holds that scan (a scan sits in ~14 windows at stride 5, 71 at stride 1).
+struct VxScanWork {
   const float4* points;
   const uint32_t* labels;
   uint32_t n;
-  uint32_t slot;
+  uint32_t use_begin;  // into the launch's VxScanUse array
+  uint32_t use_count;
+  uint32_t pad;
+};
+
+struct VxScanUse {
+  uint32_t slot;      // frame of the batch
   uint32_t ap_index;  // into the batch's ap array (16 floats each)
   uint32_t both;      // 1: prior scan -> input AND target grid; 0: past scan -> target only
 };

@@ -1,4 +1,4 @@
-// K1 + K2 (fill), K3 (vote), K5 (emit / pack): the HBM-bound passes of the gen_data hot path.
+// K1 + K2 (fill), K3 (vote), K5 (emit / pack): the HBM-side passes of the gen_data hot path.
 //
 //   fill  = fillVoxelGrid + VoxelGrid::insert     voxelize_utils.cpp:173-203, VoxelGrid.cpp:45-63
 //   vote  = majority label of saveVoxelGrid        voxelize_utils.cpp:237-245
@@ -8,6 +8,13 @@
 // All fp32 arithmetic that decides which voxel a point falls into is written with the
 // round-to-nearest intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn): the compiler never
 // contracts those into FMAs, which is what reproduces the reference's SSE2 (FMA-free) Eigen code.
+//
+// The reference re-reads a frame's whole window for every frame (180 MB of points per frame).  Here the
+// fill is organised by SCAN: a CTA loads a tile of a scan ONCE into registers, applies the
+// frame-independent filters once, and then walks the frames of the launch whose window holds that scan
+// (~14 at stride 5, 71 in the dense configuration), transforming with that frame's matrix and inserting
+// into that frame's histogram.  The histograms of the frames a scan touches (~2 MB each) stay in L2, so
+// the DRAM traffic of the pass is a fraction of its ALGORITHMIC bytes (20 B per window point per frame).
 #include "vx_launch.h"
 
 namespace {
@@ -15,163 +22,257 @@ namespace {
 constexpr int kFillThreads = 256;
 constexpr int kFillPointsPerThread = 4;
 constexpr int kFillTile = kFillThreads * kFillPointsPerThread;
+constexpr int kFillUsesPerChunk = 16;  // frames staged in shared memory at a time
 
-// (voxel,label) -> count, open addressing with linear probing.  Keys go EMPTY -> key exactly once per
-// frame, so a (possibly L1-stale) plain load is safe: a stale EMPTY is corrected by the CAS.
-__device__ __forceinline__ void table_add(const VxTable& t, unsigned long long key, uint32_t n) {
-  const uint32_t mask = (1u << t.log2_cap) - 1u;
-  uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64u - t.log2_cap));
+__device__ __forceinline__ uint32_t hash_slot(unsigned long long key, uint32_t log2_cap) {
+  return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64u - log2_cap));
+}
+
+// (voxel,label) -> count.  `seen` = the slot's key as loaded earlier by the caller (possibly stale: a
+// stale 0 is corrected by the CAS).  Keys go 0 -> key exactly once per frame.
+__device__ __forceinline__ void table_add(unsigned long long* keys, uint32_t* counts, uint32_t log2_cap, uint32_t* overflow,
+                                          unsigned long long key1, uint32_t h, unsigned long long seen, uint32_t n) {
+  const uint32_t mask = (1u << log2_cap) - 1u;
   for (uint32_t probe = 0; probe < VX_MAX_PROBES; ++probe) {
-    unsigned long long k = t.keys[h];
-    if (k == VX_EMPTY_KEY) {
-      k = atomicCAS(&t.keys[h], VX_EMPTY_KEY, key);
-      if (k == VX_EMPTY_KEY) {
-        const uint32_t u = atomicAdd(t.used_count, 1u);
-        t.used[u] = h;
-        k = key;
-      }
+    if (seen == 0ull) {
+      seen = atomicCAS(&keys[h], 0ull, key1);
+      if (seen == 0ull) seen = key1;
     }
-    if (k == key) {
-      atomicAdd(&t.counts[h], n);
+    if (seen == key1) {
+      atomicAdd(&counts[h], n);
       return;
     }
     h = (h + 1u) & mask;
+    seen = __ldcg(&keys[h]);
   }
-  atomicExch(t.overflow, 1u);
+  atomicExch(overflow, 1u);
 }
+
+struct FillUse {  // one frame a scan goes into, staged in shared memory
+  float m[12];    // rows 0..2 of ap, column-major: m[c*3 + r]
+  unsigned long long* keys_t;
+  uint32_t* counts_t;
+  uint32_t* ovf_t;
+  unsigned long long* keys_i;
+  uint32_t* counts_i;
+  uint32_t* ovf_i;
+  uint32_t log2_t, log2_i;
+  uint32_t both, pad;
+};
 
 __global__ void __launch_bounds__(kFillThreads)
-vx_fill_kernel(const VxFillItem* __restrict__ items, const float* __restrict__ ap_all, const VxSlot* __restrict__ slots,
-               const VxGridGeom g, const VxFilterDev f) {
-  const VxFillItem it = items[blockIdx.y];
+vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict__ uses, const float* __restrict__ ap_all,
+               const VxSlot* __restrict__ slots, const VxGridGeom g, const VxFilterDev f) {
+  __shared__ FillUse su[kFillUsesPerChunk];
+  const VxScanWork w = works[blockIdx.y];
   const uint32_t base = blockIdx.x * kFillTile;
-  if (base >= it.n) return;
+  if (base >= w.n) return;
+  const uint32_t lane = threadIdx.x & 31u;
 
-  const float* __restrict__ m = ap_all + 16u * it.ap_index;  // column-major: m[c*4 + r]
-  const float m00 = m[0], m10 = m[1], m20 = m[2];
-  const float m01 = m[4], m11 = m[5], m21 = m[6];
-  const float m02 = m[8], m12 = m[9], m22 = m[10];
-  const float m03 = m[12], m13 = m[13], m23 = m[14];
-  const VxSlot& slot = slots[it.slot];
-
-  float4 p[kFillPointsPerThread];
+  // ---- the tile, once: points, labels, frame-independent filters (voxelize_utils.cpp:186-198)
+  float px[kFillPointsPerThread], py[kFillPointsPerThread], pz[kFillPointsPerThread];
   uint32_t lab[kFillPointsPerThread];
-  bool valid[kFillPointsPerThread];
+  uint32_t keep0 = 0;
+  {
+    float4 p[kFillPointsPerThread];
 #pragma unroll
-  for (int u = 0; u < kFillPointsPerThread; ++u) {
-    const uint32_t idx = base + u * kFillThreads + threadIdx.x;
-    valid[u] = idx < it.n;
-    if (valid[u]) {
-      p[u] = __ldcs(it.points + idx);   // streamed once per frame: evict-first
-      lab[u] = __ldcs(it.labels + idx);
+    for (int u = 0; u < kFillPointsPerThread; ++u) {
+      const uint32_t idx = base + u * kFillThreads + threadIdx.x;
+      p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      lab[u] = 0;
+      if (idx < w.n) {
+        p[u] = __ldcs(w.points + idx);  // a scan is streamed once per launch: evict-first
+        lab[u] = __ldcs(w.labels + idx) & 0xFFFFu;
+        keep0 |= 1u << u;
+      }
     }
-  }
-
 #pragma unroll
-  for (int u = 0; u < kFillPointsPerThread; ++u) {
-    bool keep = valid[u];
-    unsigned long long key = 0;
-    if (keep) {
+    for (int u = 0; u < kFillPointsPerThread; ++u) {
       const float x = p[u].x, y = p[u].y, z = p[u].z;
-      // voxelize_utils.cpp:188  Eigen norm: sqrtf(x*x + (y*y + z*z))
+      px[u] = x;
+      py[u] = y;
+      pz[u] = z;
+      bool keep = (keep0 >> u) & 1u;
+      // voxelize_utils.cpp:188  Eigen norm: sqrtf(x*x + (y*y + z*z)); a NaN range passes, as in the reference
       const float range = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))));
-      if (range < f.min_range || range > f.max_range) keep = false;  // NaN range passes, as in the reference
+      if (range < f.min_range || range > f.max_range) keep = false;
       // voxelize_utils.cpp:190  ego-vehicle box
       if (f.hidecar && x < 3.0f && x > -2.0f && fabsf(y) < 2.0f) keep = false;
-      if (keep && f.has_label_filter) {  // voxelize_utils.cpp:195-198 (join, then ignore) as a 64 Ki-bit LUT
-        const uint32_t l16 = lab[u] & 0xFFFFu;
-        if ((__ldg(f.reject_bits + (l16 >> 5)) >> (l16 & 31u)) & 1u) keep = false;
-      }
-      if (keep) {
-        // voxelize_utils.cpp:193  ((m_r0*x + m_r1*y) + m_r2*z) + m_r3
-        const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, x), __fmul_rn(m01, y)), __fmul_rn(m02, z)), m03);
-        const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, x), __fmul_rn(m11, y)), __fmul_rn(m12, z)), m13);
-        const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, x), __fmul_rn(m21, y)), __fmul_rn(m22, z)), m23);
-        // VoxelGrid.cpp:46-53  floor((p - offset) / resolution), IEEE division; NaN / out of range rejected
-        const float fi = floorf(__fdiv_rn(__fsub_rn(px, g.off[0]), g.res));
-        const float fj = floorf(__fdiv_rn(__fsub_rn(py, g.off[1]), g.res));
-        const float fk = floorf(__fdiv_rn(__fsub_rn(pz, g.off[2]), g.res));
-        keep = (fi >= 0.0f) && (fi < (float)g.nx) && (fj >= 0.0f) && (fj < (float)g.ny) && (fk >= 0.0f) && (fk < (float)g.nz);
-        if (keep) {
-          const uint32_t L = ((uint32_t)fi * (uint32_t)g.ny + (uint32_t)fj) * (uint32_t)g.nz + (uint32_t)fk;
-          key = ((unsigned long long)L << 16) | (unsigned long long)(lab[u] & 0xFFFFu);
-        }
-      }
+      // voxelize_utils.cpp:195-198 (join, then ignore) as a 64 Ki-bit LUT over the masked label
+      if (keep && f.has_label_filter && ((__ldg(f.reject_bits + (lab[u] >> 5)) >> (lab[u] & 31u)) & 1u)) keep = false;
+      if (!keep) keep0 &= ~(1u << u);
     }
-    // K2: one atomic per distinct (voxel,label) per warp.  Scan order is beam-major / azimuth-minor,
-    // so neighbouring lanes mostly share a voxel.
-    const uint32_t active = __ballot_sync(0xFFFFFFFFu, keep);
-    if (keep) {
-      const uint32_t peers = __match_any_sync(active, key);
-      if ((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) {
-        const uint32_t n = (uint32_t)__popc(peers);
-        table_add(slot.target, key, n);
-        if (it.both) table_add(slot.input, key, n);
+  }
+  if (__syncthreads_or(keep0 != 0u) == 0) return;  // nothing of this tile survives the filters
+
+  const float fnx = (float)g.nx, fny = (float)g.ny, fnz = (float)g.nz;
+  for (uint32_t q0 = 0; q0 < w.use_count; q0 += kFillUsesPerChunk) {
+    const uint32_t nq = min((uint32_t)kFillUsesPerChunk, w.use_count - q0);
+    __syncthreads();  // the previous chunk has been consumed
+    if (threadIdx.x < nq) {
+      const VxScanUse use = uses[w.use_begin + q0 + threadIdx.x];
+      const VxSlot& s = slots[use.slot];
+      const float* m = ap_all + 16u * use.ap_index;  // column-major 4x4: m[c*4 + r]
+      FillUse& d = su[threadIdx.x];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) d.m[c * 3 + r] = m[c * 4 + r];
+      d.keys_t = s.target.keys;
+      d.counts_t = s.target.counts;
+      d.ovf_t = s.target.overflow;
+      d.log2_t = s.target.log2_cap;
+      d.keys_i = s.input.keys;
+      d.counts_i = s.input.counts;
+      d.ovf_i = s.input.overflow;
+      d.log2_i = s.input.log2_cap;
+      d.both = use.both;
+    }
+    __syncthreads();
+
+    for (uint32_t q = 0; q < nq; ++q) {
+      const FillUse& d = su[q];
+      const float m00 = d.m[0], m10 = d.m[1], m20 = d.m[2];
+      const float m01 = d.m[3], m11 = d.m[4], m21 = d.m[5];
+      const float m02 = d.m[6], m12 = d.m[7], m22 = d.m[8];
+      const float m03 = d.m[9], m13 = d.m[10], m23 = d.m[11];
+      const uint32_t log2_t = d.log2_t;
+
+      // ---- K1: key of every point of the tile in this frame
+      unsigned long long key1[kFillPointsPerThread];  // (L << 16 | label) + 1, 0 = not inserted
+#pragma unroll
+      for (int u = 0; u < kFillPointsPerThread; ++u) {
+        const float x = px[u], y = py[u], z = pz[u];
+        // voxelize_utils.cpp:193  ((m_r0*x + m_r1*y) + m_r2*z) + m_r3
+        const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, x), __fmul_rn(m01, y)), __fmul_rn(m02, z)), m03);
+        const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, x), __fmul_rn(m11, y)), __fmul_rn(m12, z)), m13);
+        const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, x), __fmul_rn(m21, y)), __fmul_rn(m22, z)), m23);
+        // VoxelGrid.cpp:46-53  floor((p - offset) / resolution), IEEE division; NaN / out of range rejected
+        const float fi = floorf(__fdiv_rn(__fsub_rn(tx, g.off[0]), g.res));
+        const float fj = floorf(__fdiv_rn(__fsub_rn(ty, g.off[1]), g.res));
+        const float fk = floorf(__fdiv_rn(__fsub_rn(tz, g.off[2]), g.res));
+        const bool in = ((keep0 >> u) & 1u) && (fi >= 0.0f) && (fi < fnx) && (fj >= 0.0f) && (fj < fny) && (fk >= 0.0f) && (fk < fnz);
+        const uint32_t L = ((uint32_t)fi * (uint32_t)g.ny + (uint32_t)fj) * (uint32_t)g.nz + (uint32_t)fk;
+        key1[u] = in ? ((((unsigned long long)L << 16) | (unsigned long long)lab[u]) + 1ull) : 0ull;
+      }
+
+      // ---- K2: one table update per RUN of equal keys in a warp row (scan order is beam-major /
+      // azimuth-minor: neighbouring lanes mostly share a voxel).  All probes of a thread are in flight together.
+      uint32_t runlen[kFillPointsPerThread], slot_t[kFillPointsPerThread];
+      unsigned long long seen_t[kFillPointsPerThread];
+#pragma unroll
+      for (int u = 0; u < kFillPointsPerThread; ++u) {
+        const unsigned long long prev = __shfl_up_sync(0xFFFFFFFFu, key1[u], 1);
+        const bool lead = key1[u] != 0ull && (lane == 0u || prev != key1[u]);
+        const uint32_t starts = __ballot_sync(0xFFFFFFFFu, lead || key1[u] == 0ull);  // a new run, or a gap, begins here
+        const uint32_t after = lane == 31u ? 0u : (starts >> (lane + 1u));
+        runlen[u] = lead ? (after ? (uint32_t)__ffs(after) : 32u - lane) : 0u;
+        slot_t[u] = hash_slot(key1[u], log2_t);
+        seen_t[u] = 0ull;
+        if (runlen[u]) seen_t[u] = __ldcg(d.keys_t + slot_t[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kFillPointsPerThread; ++u)
+        if (runlen[u]) table_add(d.keys_t, d.counts_t, log2_t, d.ovf_t, key1[u], slot_t[u], seen_t[u], runlen[u]);
+      if (d.both) {  // prior scans also fill the input grid (gen_data.cpp:96-97)
+#pragma unroll
+        for (int u = 0; u < kFillPointsPerThread; ++u)
+          if (runlen[u]) {
+            const uint32_t h = hash_slot(key1[u], d.log2_i);
+            table_add(d.keys_i, d.counts_i, d.log2_i, d.ovf_i, key1[u], h, __ldcg(d.keys_i + h), runlen[u]);
+          }
       }
     }
   }
 }
 
-// K3.  best[L] = max over labels of (count << 16 | 0xFFFF - label): largest count, ties -> smallest
-// label -- the result of scanning the reference's std::map in ascending label order with a strict '>'.
+// bit b of a 32-voxel word = voxel L0 + b.  pack() puts element 8n in bit 7 of byte n: reverse the
+// bits of every byte = reverse the word, then swap its bytes back.
+__device__ __forceinline__ uint32_t msb_first(uint32_t word) { return __byte_perm(__brev(word), 0u, 0x0123u); }
+
+// K3a.  Zeroes the dense per-frame outputs the vote scatters into (.label, occupancy, .bin).
+__global__ void __launch_bounds__(256) vx_clear_kernel(const VxSlot* __restrict__ slots, uint64_t nvox, uint32_t words) {
+  const VxSlot& s = slots[blockIdx.y];
+  const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  uint4* lab4 = reinterpret_cast<uint4*>(s.out_label);  // arenas are 256-byte aligned
+  const uint64_t n4 = nvox / 8;
+  for (uint64_t x = t0; x < n4; x += stride) lab4[x] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint64_t x = n4 * 8 + t0; x < nvox; x += stride) s.out_label[x] = 0;
+  for (uint32_t x = t0; x < words; x += stride) {
+    s.occ[x] = 0u;
+    s.out_bin[x] = 0u;
+  }
+}
+
+// K3b.  Histogram slots -> per-voxel winner: vbest[L] = max over labels of (count << 16 | 0xFFFF - label):
+// largest count, ties -> smallest label -- the result of scanning the reference's std::map in ascending
+// label order with a strict '>' (voxelize_utils.cpp:237-245).  Frees the histogram slot unless kept.
 __global__ void __launch_bounds__(256) vx_vote_kernel(const VxSlot* __restrict__ slots, int keep_tables) {
+  const VxSlot& s = slots[blockIdx.y >> 1];
+  const VxTable& t = (blockIdx.y & 1u) ? s.target : s.input;
+  const uint32_t cap = 1u << t.log2_cap, vlog2 = t.log2_cap - 1u, vmask = (cap >> 1) - 1u;
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += gridDim.x * blockDim.x) {
+    const unsigned long long k1 = __ldcs(&t.keys[h]);
+    if (k1 == 0ull) continue;
+    const unsigned long long c = t.counts[h];
+    if (!keep_tables) {
+      t.keys[h] = 0ull;
+      t.counts[h] = 0u;
+    }
+    const unsigned long long key = k1 - 1ull;
+    const uint32_t L1 = (uint32_t)(key >> 16) + 1u;
+    const unsigned long long val = (c << 16) | (0xFFFFull - (key & 0xFFFFull));
+    uint32_t v = hash_slot((unsigned long long)L1, vlog2);
+    bool done = false;
+    for (uint32_t probe = 0; probe < VX_MAX_PROBES && !done; ++probe) {
+      uint32_t seen = __ldcg(&t.vkeys[v]);
+      if (seen == 0u) {
+        seen = atomicCAS(&t.vkeys[v], 0u, L1);
+        if (seen == 0u) seen = L1;
+      }
+      if (seen == L1) {
+        atomicMax(&t.vbest[v], val);
+        done = true;
+      }
+      v = (v + 1u) & vmask;
+    }
+    if (!done) atomicExch(t.overflow, 1u);
+  }
+}
+
+// K5a.  Winner slots -> .label (uint16), occupancy bit (target grid), .bin bit (input grid, majority
+// label > 0, MSB-first).  Frees the winner slot.
+__global__ void __launch_bounds__(256) vx_emit_kernel(const VxSlot* __restrict__ slots) {
   const VxSlot& s = slots[blockIdx.y >> 1];
   const bool is_target = (blockIdx.y & 1u) != 0;
   const VxTable& t = is_target ? s.target : s.input;
-  unsigned long long* best = is_target ? s.best_target : s.best_input;
-  const uint32_t used = *t.used_count;
-  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < used; u += gridDim.x * blockDim.x) {
-    const uint32_t h = t.used[u];
-    const unsigned long long key = t.keys[h];
-    const unsigned long long c = t.counts[h];
-    const unsigned long long L = key >> 16;
-    const unsigned long long label = key & 0xFFFFull;
-    atomicMax(&best[L], (c << 16) | (0xFFFFull - label));
-    if (!keep_tables) {
-      t.keys[h] = VX_EMPTY_KEY;
-      t.counts[h] = 0;
+  const uint32_t vcap = 1u << (t.log2_cap - 1u);
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < vcap; v += gridDim.x * blockDim.x) {
+    const uint32_t L1 = __ldcs(&t.vkeys[v]);
+    if (L1 == 0u) continue;
+    const unsigned long long best = t.vbest[v];
+    t.vkeys[v] = 0u;
+    t.vbest[v] = 0ull;
+    const uint32_t L = L1 - 1u;
+    const uint32_t label = 0xFFFFu - (uint32_t)(best & 0xFFFFull);
+    if (is_target) {
+      s.out_label[L] = (uint16_t)label;
+      atomicOr(&s.occ[L >> 5], 1u << (L & 31u));  // occupied = count > 0, whatever the label (VoxelGrid.cpp:45-63)
+    } else if (label > 0u) {
+      const uint32_t b = L & 31u;
+      atomicOr(&s.out_bin[L >> 5], 1u << ((b & 24u) | (7u - (b & 7u))));  // element 8n + e -> byte n, bit 7 - e
     }
   }
 }
 
+// Frees tables that were kept for debugging.
 __global__ void __launch_bounds__(256) vx_table_reset_kernel(const VxSlot* __restrict__ slots) {
   const VxSlot& s = slots[blockIdx.y >> 1];
   const VxTable& t = (blockIdx.y & 1u) ? s.target : s.input;
-  const uint32_t used = *t.used_count;
-  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < used; u += gridDim.x * blockDim.x) {
-    const uint32_t h = t.used[u];
-    t.keys[h] = VX_EMPTY_KEY;
-    t.counts[h] = 0;
-  }
-}
-
-// bit b of a 32-voxel ballot = voxel L0 + b.  pack() puts element 8n in bit 7 of byte n: reverse the
-// bits of every byte = reverse the word, then swap its bytes back.
-__device__ __forceinline__ uint32_t msb_first(uint32_t ballot) { return __byte_perm(__brev(ballot), 0u, 0x0123u); }
-
-// K5a.  One warp per 32 consecutive voxels.
-__global__ void __launch_bounds__(256) vx_emit_kernel(const VxSlot* __restrict__ slots, uint64_t nvox) {
-  const VxSlot& s = slots[blockIdx.y];
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-  for (uint64_t L0 = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; L0 < nvox; L0 += warps * 32u) {
-    const uint64_t L = L0 + lane;
-    const bool valid = L < nvox;
-    unsigned long long bi = 0, bt = 0;
-    if (valid) {
-      bi = s.best_input[L];
-      bt = s.best_target[L];
-      if (bi) s.best_input[L] = 0;
-      if (bt) s.best_target[L] = 0;
-      s.out_label[L] = bt ? (uint16_t)(0xFFFFu - (uint32_t)(bt & 0xFFFFull)) : (uint16_t)0;
-    }
-    const uint32_t label_in = bi ? (0xFFFFu - (uint32_t)(bi & 0xFFFFull)) : 0u;
-    const uint32_t occ_word = __ballot_sync(0xFFFFFFFFu, bt != 0);
-    const uint32_t bin_word = __ballot_sync(0xFFFFFFFFu, label_in > 0u);
-    if (lane == 0) {
-      s.occ[L0 >> 5] = occ_word;
-      s.out_bin[L0 >> 5] = msb_first(bin_word);
-    }
+  const uint32_t cap = 1u << t.log2_cap;
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += gridDim.x * blockDim.x) {
+    t.keys[h] = 0ull;
+    t.counts[h] = 0u;
   }
 }
 
@@ -188,35 +289,34 @@ __global__ void __launch_bounds__(256) vx_pack_kernel(const VxSlot* __restrict__
 
 }  // namespace
 
-cudaError_t vx_launch_fill(const VxFillItem* items, uint32_t n_items, uint32_t max_points, const float* ap,
+cudaError_t vx_launch_fill(const VxScanWork* works, uint32_t n_works, uint32_t max_points, const VxScanUse* uses, const float* ap,
                            const VxSlot* slots, VxGridGeom geom, VxFilterDev filter, cudaStream_t stream) {
-  if (n_items == 0 || max_points == 0) return cudaSuccess;
+  if (n_works == 0 || max_points == 0) return cudaSuccess;
   const uint32_t tiles = (max_points + kFillTile - 1) / kFillTile;
-  for (uint32_t first = 0; first < n_items; first += 65535u) {
-    const uint32_t n = n_items - first < 65535u ? n_items - first : 65535u;
-    vx_fill_kernel<<<dim3(tiles, n), kFillThreads, 0, stream>>>(items + first, ap, slots, geom, filter);
+  for (uint32_t first = 0; first < n_works; first += 65535u) {
+    const uint32_t n = n_works - first < 65535u ? n_works - first : 65535u;
+    vx_fill_kernel<<<dim3(tiles, n), kFillThreads, 0, stream>>>(works + first, uses, ap, slots, geom, filter);
   }
   return cudaGetLastError();
 }
 
-cudaError_t vx_launch_vote(const VxSlot* slots, uint32_t n_slots, int keep_tables, cudaStream_t stream) {
+cudaError_t vx_launch_vote(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, int keep_tables, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
-  vx_vote_kernel<<<dim3(32, 2 * n_slots), 256, 0, stream>>>(slots, keep_tables);
+  const uint32_t words = (uint32_t)((nvox + 31) / 32);
+  vx_clear_kernel<<<dim3(64, n_slots), 256, 0, stream>>>(slots, nvox, words);
+  vx_vote_kernel<<<dim3(64, 2 * n_slots), 256, 0, stream>>>(slots, keep_tables);
   return cudaGetLastError();
 }
 
 cudaError_t vx_launch_table_reset(const VxSlot* slots, uint32_t n_slots, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
-  vx_table_reset_kernel<<<dim3(32, 2 * n_slots), 256, 0, stream>>>(slots);
+  vx_table_reset_kernel<<<dim3(64, 2 * n_slots), 256, 0, stream>>>(slots);
   return cudaGetLastError();
 }
 
-cudaError_t vx_launch_emit(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, cudaStream_t stream) {
+cudaError_t vx_launch_emit(const VxSlot* slots, uint32_t n_slots, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
-  const uint64_t warps_needed = (nvox + 31) / 32;
-  uint32_t blocks = (uint32_t)((warps_needed + 7) / 8);
-  if (blocks > 1024u) blocks = 1024u;
-  vx_emit_kernel<<<dim3(blocks, n_slots), 256, 0, stream>>>(slots, nvox);
+  vx_emit_kernel<<<dim3(32, 2 * n_slots), 256, 0, stream>>>(slots);
   return cudaGetLastError();
 }
 
