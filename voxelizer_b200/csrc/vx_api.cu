@@ -128,10 +128,10 @@ void derive_geometry(const vx_grid_desc& d, VxGridGeom& g) {
 
 size_t table_bytes(uint32_t log2_cap) {
   const size_t cap = (size_t)1 << log2_cap;
-  return align_up(cap * 8, 256) + align_up(cap * 4, 256) + align_up(cap / 2 * 4, 256) + align_up(cap / 2 * 8, 256);
+  return align_up(cap * 8, 256) + align_up(cap * 4, 256);
 }
 
-size_t table_set_bytes(const vx_ctx* c) { return table_bytes(c->log2_target) + table_bytes(c->log2_input); }
+size_t table_set_bytes(const vx_ctx* c) { return table_bytes(c->log2_target) + table_bytes(c->log2_input) + 2 * align_up(c->nvox * 8, 256); }
 
 size_t frame_bytes(const vx_ctx* c) { return 6 * align_up((size_t)c->words * 4, 256) + align_up(c->nvox * 2, 256); }
 
@@ -154,8 +154,7 @@ int alloc_table_set(vx_ctx* c, TableSet& t) {
     const size_t cap = (size_t)1 << log2_cap;
     tb.keys = reinterpret_cast<unsigned long long*>(cv.take(cap * 8));
     tb.counts = reinterpret_cast<uint32_t*>(cv.take(cap * 4));
-    tb.vkeys = reinterpret_cast<uint32_t*>(cv.take(cap / 2 * 4));
-    tb.vbest = reinterpret_cast<unsigned long long*>(cv.take(cap / 2 * 8));
+    tb.best = reinterpret_cast<unsigned long long*>(cv.take(c->nvox * 8));
     tb.log2_cap = log2_cap;
   };
   carve(t.target, c->log2_target);
@@ -375,9 +374,9 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 0], st));
     VX_CUDA(c, vx_launch_fill(d_works + work_begin[g], n_works, sub_max_points[g], d_uses, d_ap, c->d_slots, c->geom, c->filter, st));
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 1], st));
-    VX_CUDA(c, vx_launch_vote(c->d_slots + f0, f1 - f0, c->nvox, c->keep_tables ? 1 : 0, st));
+    VX_CUDA(c, vx_launch_vote(c->d_slots + f0, f1 - f0, c->nvox, st));
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 2], st));
-    VX_CUDA(c, vx_launch_emit(c->d_slots + f0, f1 - f0, st));
+    VX_CUDA(c, vx_launch_emit(c->d_slots + f0, f1 - f0, c->keep_tables ? 1 : 0, st));
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 3], st));
     fill_launches += (n_works + 65534) / 65535;
   }

@@ -16,15 +16,14 @@
 #define VX_MAX_PROBES 4096u
 #define VX_SLOT_STATS 13
 
-// Open-addressing histogram of one grid of one frame: (L << 16 | label16) -> count, and the per-voxel
-// winner table the vote builds from it: L -> max(count << 16 | 0xFFFF - label).  Keys are stored + 1 so
-// that an all-zero table is empty.
+// Open-addressing histogram of one grid of one frame: (L << 16 | label16) -> count, and the dense
+// per-voxel vote array best[L] = max over labels of (count << 16 | 0xFFFF - label).  Keys are stored + 1
+// so that an all-zero table is empty; best[] is zero outside a vote (the winners reset their entries).
 struct VxTable {
-  unsigned long long* keys;   // [cap]   ((L << 16 | label) + 1), 0 = free
+  unsigned long long* keys;   // [cap]  ((L << 16 | label) + 1), 0 = free
   uint32_t* counts;           // [cap]
-  uint32_t* vkeys;            // [cap/2] (L + 1), 0 = free
-  unsigned long long* vbest;  // [cap/2]
-  uint32_t* overflow;         // [1] set when a probe sequence ran out (either table)
+  unsigned long long* best;   // [nvox]
+  uint32_t* overflow;         // [1] set when a probe sequence ran out
   uint32_t log2_cap;
 };
 

@@ -24,8 +24,23 @@ constexpr int kFillPointsPerThread = 4;
 constexpr int kFillTile = kFillThreads * kFillPointsPerThread;
 constexpr int kFillUsesPerChunk = 16;  // frames staged in shared memory at a time
 
-__device__ __forceinline__ uint32_t hash_slot(unsigned long long key, uint32_t log2_cap) {
-  return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64u - log2_cap));
+// slot of key (L << 16 | label) + 1: two 32-bit multiplicative mixes (L and label are < 2^31 and < 2^16)
+__device__ __forceinline__ uint32_t hash_slot(unsigned long long key1, uint32_t log2_cap) {
+  const uint32_t lo = (uint32_t)key1, hi = (uint32_t)(key1 >> 16);
+  return ((hi * 0x9E3779B1u) ^ (lo * 0x85EBCA77u)) >> (32u - log2_cap);
+}
+
+// floorf(__fdiv_rn(v, res)) without the division in the common case.  q0 = v * rcp (rcp = RN(1/res)) is
+// within 1.5 * 2^-23 relative of the correctly rounded quotient, so when q0 is further than 2^-21 |q0|
+// from both neighbouring integers the two have the same floor; otherwise (about 1 point in 10^4), and for
+// NaN / infinity, the IEEE division decides.
+__device__ __forceinline__ float floor_div(float v, float res, float rcp) {
+  const float q0 = __fmul_rn(v, rcp);
+  const float n = floorf(q0);
+  const float d = q0 - n;                            // exact: q0 and n share the exponent range
+  const float margin = fabsf(q0) * 4.76837158e-7f;   // 2^-21 |q0|
+  if (d > margin && (1.0f - d) > margin) return n;
+  return floorf(__fdiv_rn(v, res));
 }
 
 // (voxel,label) -> count.  `seen` = the slot's key as loaded earlier by the caller (possibly stale: a
@@ -106,6 +121,7 @@ vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict
   if (__syncthreads_or(keep0 != 0u) == 0) return;  // nothing of this tile survives the filters
 
   const float fnx = (float)g.nx, fny = (float)g.ny, fnz = (float)g.nz;
+  const float rcp = __frcp_rn(g.res);
   for (uint32_t q0 = 0; q0 < w.use_count; q0 += kFillUsesPerChunk) {
     const uint32_t nq = min((uint32_t)kFillUsesPerChunk, w.use_count - q0);
     __syncthreads();  // the previous chunk has been consumed
@@ -148,9 +164,9 @@ vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict
         const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, x), __fmul_rn(m11, y)), __fmul_rn(m12, z)), m13);
         const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, x), __fmul_rn(m21, y)), __fmul_rn(m22, z)), m23);
         // VoxelGrid.cpp:46-53  floor((p - offset) / resolution), IEEE division; NaN / out of range rejected
-        const float fi = floorf(__fdiv_rn(__fsub_rn(tx, g.off[0]), g.res));
-        const float fj = floorf(__fdiv_rn(__fsub_rn(ty, g.off[1]), g.res));
-        const float fk = floorf(__fdiv_rn(__fsub_rn(tz, g.off[2]), g.res));
+        const float fi = floor_div(__fsub_rn(tx, g.off[0]), g.res, rcp);
+        const float fj = floor_div(__fsub_rn(ty, g.off[1]), g.res, rcp);
+        const float fk = floor_div(__fsub_rn(tz, g.off[2]), g.res, rcp);
         const bool in = ((keep0 >> u) & 1u) && (fi >= 0.0f) && (fi < fnx) && (fj >= 0.0f) && (fj < fny) && (fk >= 0.0f) && (fk < fnz);
         const uint32_t L = ((uint32_t)fi * (uint32_t)g.ny + (uint32_t)fj) * (uint32_t)g.nz + (uint32_t)fk;
         key1[u] = in ? ((((unsigned long long)L << 16) | (unsigned long long)lab[u]) + 1ull) : 0ull;
@@ -204,63 +220,78 @@ __global__ void __launch_bounds__(256) vx_clear_kernel(const VxSlot* __restrict_
   }
 }
 
-// K3b.  Histogram slots -> per-voxel winner: vbest[L] = max over labels of (count << 16 | 0xFFFF - label):
-// largest count, ties -> smallest label -- the result of scanning the reference's std::map in ascending
-// label order with a strict '>' (voxelize_utils.cpp:237-245).  Frees the histogram slot unless kept.
-__global__ void __launch_bounds__(256) vx_vote_kernel(const VxSlot* __restrict__ slots, int keep_tables) {
+constexpr int kScanBatch = 8;  // histogram slots a thread has in flight (the scans are latency-bound otherwise)
+
+// K3b.  best[L] = max over the labels of voxel L of (count << 16 | 0xFFFF - label): largest count, ties ->
+// smallest label -- the result of scanning the reference's std::map in ascending label order with a
+// strict '>' (voxelize_utils.cpp:237-245).  One fire-and-forget RED per histogram slot.
+__global__ void __launch_bounds__(256) vx_vote_kernel(const VxSlot* __restrict__ slots) {
   const VxSlot& s = slots[blockIdx.y >> 1];
   const VxTable& t = (blockIdx.y & 1u) ? s.target : s.input;
-  const uint32_t cap = 1u << t.log2_cap, vlog2 = t.log2_cap - 1u, vmask = (cap >> 1) - 1u;
-  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += gridDim.x * blockDim.x) {
-    const unsigned long long k1 = __ldcs(&t.keys[h]);
-    if (k1 == 0ull) continue;
-    const unsigned long long c = t.counts[h];
-    if (!keep_tables) {
-      t.keys[h] = 0ull;
-      t.counts[h] = 0u;
+  const uint32_t cap = 1u << t.log2_cap;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t h0 = blockIdx.x * blockDim.x + threadIdx.x; h0 < cap; h0 += stride * kScanBatch) {
+    unsigned long long k1[kScanBatch];
+    uint32_t c[kScanBatch];
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u) {
+      const uint32_t h = h0 + (uint32_t)u * stride;
+      k1[u] = h < cap ? __ldcg(&t.keys[h]) : 0ull;
+      c[u] = h < cap ? __ldcg(&t.counts[h]) : 0u;
     }
-    const unsigned long long key = k1 - 1ull;
-    const uint32_t L1 = (uint32_t)(key >> 16) + 1u;
-    const unsigned long long val = (c << 16) | (0xFFFFull - (key & 0xFFFFull));
-    uint32_t v = hash_slot((unsigned long long)L1, vlog2);
-    bool done = false;
-    for (uint32_t probe = 0; probe < VX_MAX_PROBES && !done; ++probe) {
-      uint32_t seen = __ldcg(&t.vkeys[v]);
-      if (seen == 0u) {
-        seen = atomicCAS(&t.vkeys[v], 0u, L1);
-        if (seen == 0u) seen = L1;
-      }
-      if (seen == L1) {
-        atomicMax(&t.vbest[v], val);
-        done = true;
-      }
-      v = (v + 1u) & vmask;
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u) {
+      if (k1[u] == 0ull) continue;
+      const unsigned long long key = k1[u] - 1ull;
+      atomicMax(&t.best[key >> 16], ((unsigned long long)c[u] << 16) | (0xFFFFull - (key & 0xFFFFull)));
     }
-    if (!done) atomicExch(t.overflow, 1u);
   }
 }
 
-// K5a.  Winner slots -> .label (uint16), occupancy bit (target grid), .bin bit (input grid, majority
-// label > 0, MSB-first).  Frees the winner slot.
-__global__ void __launch_bounds__(256) vx_emit_kernel(const VxSlot* __restrict__ slots) {
+// K5a.  The slot that holds its voxel's winner writes .label (uint16), the occupancy bit (target grid) or the
+// .bin bit (input grid, majority label > 0, MSB-first) and resets best[L]; every slot is freed (unless kept).
+__global__ void __launch_bounds__(256) vx_emit_kernel(const VxSlot* __restrict__ slots, int keep_tables) {
   const VxSlot& s = slots[blockIdx.y >> 1];
   const bool is_target = (blockIdx.y & 1u) != 0;
   const VxTable& t = is_target ? s.target : s.input;
-  const uint32_t vcap = 1u << (t.log2_cap - 1u);
-  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < vcap; v += gridDim.x * blockDim.x) {
-    const uint32_t L1 = __ldcs(&t.vkeys[v]);
-    if (L1 == 0u) continue;
-    const unsigned long long best = t.vbest[v];
-    t.vkeys[v] = 0u;
-    t.vbest[v] = 0ull;
-    const uint32_t L = L1 - 1u;
-    const uint32_t label = 0xFFFFu - (uint32_t)(best & 0xFFFFull);
-    if (is_target) {
-      s.out_label[L] = (uint16_t)label;
-      atomicOr(&s.occ[L >> 5], 1u << (L & 31u));  // occupied = count > 0, whatever the label (VoxelGrid.cpp:45-63)
-    } else if (label > 0u) {
-      const uint32_t b = L & 31u;
-      atomicOr(&s.out_bin[L >> 5], 1u << ((b & 24u) | (7u - (b & 7u))));  // element 8n + e -> byte n, bit 7 - e
+  const uint32_t cap = 1u << t.log2_cap;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t h0 = blockIdx.x * blockDim.x + threadIdx.x; h0 < cap; h0 += stride * kScanBatch) {
+    unsigned long long k1[kScanBatch], b[kScanBatch];
+    uint32_t c[kScanBatch];
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u) {
+      const uint32_t h = h0 + (uint32_t)u * stride;
+      k1[u] = h < cap ? __ldcs(&t.keys[h]) : 0ull;
+      c[u] = h < cap ? __ldcs(&t.counts[h]) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u) {
+      b[u] = 0ull;
+      if (k1[u] != 0ull) {
+        b[u] = __ldcg(&t.best[(k1[u] - 1ull) >> 16]);
+        if (!keep_tables) {
+          const uint32_t h = h0 + (uint32_t)u * stride;
+          t.keys[h] = 0ull;
+          t.counts[h] = 0u;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u) {
+      if (k1[u] == 0ull) continue;
+      const unsigned long long key = k1[u] - 1ull;
+      const uint32_t L = (uint32_t)(key >> 16);
+      const uint32_t label = (uint32_t)(key & 0xFFFFull);
+      if (b[u] != (((unsigned long long)c[u] << 16) | (0xFFFFull - label))) continue;  // (count, label) pairs of a voxel are distinct
+      t.best[L] = 0ull;
+      if (is_target) {
+        s.out_label[L] = (uint16_t)label;
+        atomicOr(&s.occ[L >> 5], 1u << (L & 31u));  // occupied = count > 0, whatever the label (VoxelGrid.cpp:45-63)
+      } else if (label > 0u) {
+        const uint32_t bb = L & 31u;
+        atomicOr(&s.out_bin[L >> 5], 1u << ((bb & 24u) | (7u - (bb & 7u))));  // element 8n + e -> byte n, bit 7 - e
+      }
     }
   }
 }
@@ -300,11 +331,11 @@ cudaError_t vx_launch_fill(const VxScanWork* works, uint32_t n_works, uint32_t m
   return cudaGetLastError();
 }
 
-cudaError_t vx_launch_vote(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, int keep_tables, cudaStream_t stream) {
+cudaError_t vx_launch_vote(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
   const uint32_t words = (uint32_t)((nvox + 31) / 32);
   vx_clear_kernel<<<dim3(64, n_slots), 256, 0, stream>>>(slots, nvox, words);
-  vx_vote_kernel<<<dim3(64, 2 * n_slots), 256, 0, stream>>>(slots, keep_tables);
+  vx_vote_kernel<<<dim3(32, 2 * n_slots), 256, 0, stream>>>(slots);
   return cudaGetLastError();
 }
 
@@ -314,9 +345,9 @@ cudaError_t vx_launch_table_reset(const VxSlot* slots, uint32_t n_slots, cudaStr
   return cudaGetLastError();
 }
 
-cudaError_t vx_launch_emit(const VxSlot* slots, uint32_t n_slots, cudaStream_t stream) {
+cudaError_t vx_launch_emit(const VxSlot* slots, uint32_t n_slots, int keep_tables, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
-  vx_emit_kernel<<<dim3(32, 2 * n_slots), 256, 0, stream>>>(slots);
+  vx_emit_kernel<<<dim3(32, 2 * n_slots), 256, 0, stream>>>(slots, keep_tables);
   return cudaGetLastError();
 }
 

@@ -9,13 +9,14 @@
 cudaError_t vx_launch_fill(const VxScanWork* works, uint32_t n_works, uint32_t max_points, const VxScanUse* uses, const float* ap,
                            const VxSlot* slots, VxGridGeom geom, VxFilterDev filter, cudaStream_t stream);
 
-// K3: clears the dense outputs, then histogram slots -> per-voxel winner table (frees the slots unless keep_tables).
-cudaError_t vx_launch_vote(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, int keep_tables, cudaStream_t stream);
+// K3: clears the dense outputs, then one RED.MAX per histogram slot into the dense vote array best[L].
+cudaError_t vx_launch_vote(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, cudaStream_t stream);
 // Frees tables that were kept for debugging.
 cudaError_t vx_launch_table_reset(const VxSlot* slots, uint32_t n_slots, cudaStream_t stream);
 
-// K5a: winner table -> .label (uint16), .bin (packed, input grid), occupancy bitmap; frees the winner slots.
-cudaError_t vx_launch_emit(const VxSlot* slots, uint32_t n_slots, cudaStream_t stream);
+// K5a: winning slots -> .label (uint16), .bin (packed, input grid), occupancy bitmap; frees the histogram
+// slots (unless keep_tables) and resets best[].
+cudaError_t vx_launch_emit(const VxSlot* slots, uint32_t n_slots, int keep_tables, cudaStream_t stream);
 
 // K4: occlusion pass + invalid passes, one CTA per frame; every CTA claims one of the n_scratch scratch
 // buffers (locks[i]: 0 free / 1 taken) -- n_scratch must be >= vx_visibility_resident_ctas().
