@@ -195,3 +195,30 @@ def test_unknown_scan_is_an_error():
     with pytest.raises(vx.VxError, match="not resident"):
         be.process([spec])
     be.close()
+
+
+def test_stress_grid_512(orc, tmp_path):
+    """BASELINE configs[3]: 512 x 512 x 64 @ 0.1 m -- two 32-cell chunks per column, 16x16-voxel coarse blocks,
+    16.8 M voxels.  Small scans and two invalid passes keep the oracle at a few seconds."""
+    seq = make_sequence(str(tmp_path / "seq"), 3, 32, 700)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    be = _backend("stress_512", scans, raw, frames_in_flight=1)
+    assert be.size == (512, 512, 64)
+    o = oracle_frame(orc, cfg_path("stress_512"), scans, labels, poses, [0], [1, 2])
+    p = product_frame(be, poses, [0], [1, 2])
+    assert_frames_equal(p, o)
+    be.close()
+
+
+def test_more_passes_than_memo_epochs(orc, tmp_path):
+    """BASELINE configs[4] in small: far more updateInvalid passes than the 127 pass tags of the memo, so the tag
+    counter restarts (twice) inside one frame."""
+    seq = make_sequence(str(tmp_path / "seq"), 3, 16, 300)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    rng = np.random.default_rng(3)
+    eps = np.column_stack([rng.uniform(-2, 28, 300), rng.uniform(-14, 14, 300), rng.uniform(-2.5, 5, 300)]).astype(np.float32)
+    be = _backend("test_small", scans, raw)
+    o = oracle_frame(orc, cfg_path("test_small"), scans, labels, poses, [0], [1, 2], extra_endpoints=eps)
+    p = product_frame(be, poses, [0], [1, 2], extra_endpoints=eps)
+    assert_frames_equal(p, o)
+    be.close()
