@@ -307,7 +307,7 @@ def run_ours(args):
         e_ms = e_wall_ms / max(1, args.steps)  # includes host-side staging gaps
         h2d = int(counts.sum()) * 20 + sum((len(s.prior_ids) + len(s.past_ids)) * (64 + 24) + len(s.endpoints) * 12 for s in specs)
         d2h = n_frames * per
-        e2e = {"value": total_frames / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": total_frames / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "ms_per_step": e_ms, "device_ms_per_step": e_dev_ms / max(1, args.steps)}
 
     if rank == 0:

@@ -41,7 +41,8 @@ namespace {
 
 constexpr int kVisThreads = 128;
 constexpr int kVisWarps = kVisThreads / 32;
-constexpr int kMaxLive = 1536;    // live cells per wave
+constexpr int kMaxLive = 1280;    // live cells per wave
+constexpr int kAxisTable = 560;   // nx + ny + nz entries of the per-pass ray set-up table (256 + 256 + 32 = 544)
 constexpr int kMaxChunks = 256;   // chunk = <= 32 consecutive z of one column
 constexpr int kChunksPerThread = kMaxChunks / kVisThreads;
 constexpr int kLivePerThread = kMaxLive / kVisThreads;
@@ -64,6 +65,7 @@ struct VisShared {
   uint32_t decided[kMaxLive / 32];  // per candidate slot
   uint32_t castbit[kMaxLive / 32];  // per candidate slot
   uint32_t has_succ[kMaxLive / 32]; // per candidate slot: its in-face ray crosses a later candidate
+  float axis[kAxisTable];           // per pass: +-DeltaT of a ray starting at x = i | y = j | z = k (sign = Step)
   uint32_t warp_sums[kVisWarps];
   uint32_t scan_total;
   uint32_t ncols_ok;
@@ -99,6 +101,7 @@ struct Frame {
   int32_t ex, ey, ez;  // end voxel of the pass (VoxelGrid.h:99-102: truncation)
   uint32_t epoch;
   bool inv;
+  bool tables;        // sm.axis holds this pass's ray set-up
 };
 
 __device__ __forceinline__ uint32_t lin(const VxGridGeom& g, int32_t i, int32_t j, int32_t k) {
@@ -185,10 +188,65 @@ __device__ __forceinline__ bool occupied(const Frame& f, const VisShared& sm, in
   return coarse_set(f, sm, i, j, k) && occupied_exact(f, i, j, k);
 }
 
-// The first step of the ray from (i,j,k) is certainly along `normal`: its in-face part is empty.
-// (NextCrossingT = half / |dir|, VoxelGrid.cpp:257,264: the largest |dir| steps first; the 1e-4 margin
-// is far above the rounding of the division and of the conversion to float.)
-__device__ __forceinline__ bool normal_first(const Frame& f, int32_t i, int32_t j, int32_t k, int32_t normal) {
+// Ray set-up (VoxelGrid.cpp:249-270).  DeltaT, Step and NextCrossingT of an axis depend only on that axis'
+// start coordinate and the pass's endpoint, so a pass tabulates them once (nx + ny + nz divisions) and a ray
+// starts with three shared-memory loads instead of three IEEE divisions.
+__device__ __forceinline__ void ray_begin(const Frame& f, const VisShared& sm, VxRay& r, int32_t i, int32_t j, int32_t k) {
+  if (!f.tables) {
+    r.begin(f.g, i, j, k, f.e0, f.e1, f.e2);
+    return;
+  }
+  const float vx = sm.axis[i], vy = sm.axis[f.g.nx + j], vz = sm.axis[f.g.nx + f.g.ny + k];
+  r.i = i;
+  r.j = j;
+  r.k = k;
+  r.dx = fabsf(vx);
+  r.dy = fabsf(vy);
+  r.dz = fabsf(vz);
+  r.tx = VX_FMUL(0.5f, r.dx);
+  r.ty = VX_FMUL(0.5f, r.dy);
+  r.tz = VX_FMUL(0.5f, r.dz);
+  r.sx = signbit(vx) ? -1 : 1;
+  r.sy = signbit(vy) ? -1 : 1;
+  r.sz = signbit(vz) ? -1 : 1;
+  r.ox = r.sx < 0 ? 0 : f.g.nx;
+  r.oy = r.sy < 0 ? 0 : f.g.ny;
+  r.oz = r.sz < 0 ? 0 : f.g.nz;
+  r.ex = f.ex;
+  r.ey = f.ey;
+  r.ez = f.ez;
+}
+
+// Tabulates the pass (all threads).  Leaves f.tables false when the grid is too large for the table or when
+// an entry would need the reference's special cases (subnormal DeltaT, a -0.0 direction).
+__device__ void build_axis_table(Frame& f, VisShared& sm) {
+  const int32_t total = f.g.nx + f.g.ny + f.g.nz;
+  f.tables = false;
+  if (total > kAxisTable) return;
+  bool bad = false;
+  for (int32_t x = (int32_t)threadIdx.x; x < total; x += kVisThreads) {
+    const int32_t axis = x < f.g.nx ? 0 : (x < f.g.nx + f.g.ny ? 1 : 2);
+    const int32_t c = axis == 0 ? x : (axis == 1 ? x - f.g.nx : x - f.g.nx - f.g.ny);
+    const float e = axis == 0 ? f.e0 : (axis == 1 ? f.e1 : f.e2);
+    const int32_t size = axis == 0 ? f.g.nx : (axis == 1 ? f.g.ny : f.g.nz);
+    const float off = axis == 0 ? f.g.off[0] : (axis == 1 ? f.g.off[1] : f.g.off[2]);
+    const VxAxis a = vx_axis_setup(off, f.g.res, size, c, e);
+    // the table encodes Step in the sign and relies on NextCrossingT == 0.5 * DeltaT
+    if (!(a.tdelta >= 4.0e-38f) || a.tmax != VX_FMUL(0.5f, a.tdelta)) bad = true;
+    sm.axis[x] = a.step < 0 ? -a.tdelta : a.tdelta;
+  }
+  f.tables = __syncthreads_or(bad ? 1 : 0) == 0;
+}
+
+// The first step of the ray from (i,j,k) is along `normal`: its in-face part is empty.
+__device__ __forceinline__ bool normal_first(const Frame& f, const VisShared& sm, int32_t i, int32_t j, int32_t k, int32_t normal) {
+  if (f.tables) {
+    const float tx = VX_FMUL(0.5f, fabsf(sm.axis[i])), ty = VX_FMUL(0.5f, fabsf(sm.axis[f.g.nx + j]));
+    const float tz = VX_FMUL(0.5f, fabsf(sm.axis[f.g.nx + f.g.ny + k]));
+    return vx_step_axis(tx, ty, tz) == normal;
+  }
+  // without the table: certainly along `normal` when its |dir| dominates (NextCrossingT = half / |dir|; the
+  // 1e-4 margin is far above the rounding of the division and of the conversion to float)
   const float d0 = fabsf(VX_FSUB(f.e0, vx_voxel_centre(f.g.off[0], f.g.res, i)));
   const float d1 = fabsf(VX_FSUB(f.e1, vx_voxel_centre(f.g.off[1], f.g.res, j)));
   const float d2 = fabsf(VX_FSUB(f.e2, vx_voxel_centre(f.g.off[2], f.g.res, k)));
@@ -204,7 +262,7 @@ __device__ __forceinline__ void prefix_walk(const Frame& f, const Wave& w, const
   int32_t i, j, k;
   wave_cell(f, w, sm.rcell[rc], i, j, k);
   VxRay r;
-  r.begin(f.g, i, j, k, f.e0, f.e1, f.e2);
+  ray_begin(f, sm, r, i, j, k);
   const int32_t normal = w.face == 0 ? 0 : 1;
   for (;;) {
     if (r.next_axis() == normal) return;
@@ -242,12 +300,11 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
             rc = sm.cand[s];
             id = id_base + s;
             wave_cell(f, w, sm.rcell[rc], i, j, k);
-            const VxAxis ax = vx_axis_setup(f.g.off[0], f.g.res, f.g.nx, i, f.e0);
-            const VxAxis ay = vx_axis_setup(f.g.off[1], f.g.res, f.g.ny, j, f.e1);
-            const VxAxis az = vx_axis_setup(f.g.off[2], f.g.res, f.g.nz, k, f.e2);
-            tx = ax.tmax; dx = ax.tdelta; sx = ax.step;
-            ty = ay.tmax; dy = ay.tdelta; sy = ay.step;
-            tz = az.tmax; dz = az.tdelta; sz = az.step;
+            VxRay r0;
+            ray_begin(f, sm, r0, i, j, k);
+            tx = r0.tx; dx = r0.dx; sx = r0.sx;
+            ty = r0.ty; dy = r0.dy; sy = r0.sy;
+            tz = r0.tz; dz = r0.dz; sz = r0.sz;
             L = lin(f.g, i, j, k);
             active = true;
             in_face = true;
@@ -452,7 +509,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       const uint32_t rc = sm.cand[p];
       int32_t i, j, k;
       wave_cell(f, w, sm.rcell[rc], i, j, k);
-      if (normal_first(f, i, j, k, normal)) continue;
+      if (normal_first(f, sm, i, j, k, normal)) continue;
       bool any = false;
       prefix_walk(f, w, sm, rc, [&](uint32_t x) {
         if (!(sm.owner[x] & kSet)) {
@@ -651,6 +708,7 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     f.ey = vx_trunc_i32(VX_FDIV(VX_FSUB(f.e1, g.off[1]), g.res));
     f.ez = vx_trunc_i32(VX_FDIV(VX_FSUB(f.e2, g.off[2]), g.res));
     f.epoch = (pass % kMaxEpoch) + 1u;
+    build_axis_table(f, sm);  // (barrier inside)
     if (pass % kMaxEpoch == 0) {  // first pass, or the epoch counter restarts: forget every memo
       for (uint32_t x = tid; x < nvox; x += kVisThreads) f.memo[x] = 0u;
     }
