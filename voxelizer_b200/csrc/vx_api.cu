@@ -520,8 +520,9 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
     return bail(VX_ERR_INVALID);
   }
   c->nvox = (uint64_t)c->geom.nx * (uint64_t)c->geom.ny * (uint64_t)c->geom.nz;
-  if (c->nvox >= (1ull << 31) || vx_visibility_visits(c->geom) >= (1ull << 25)) {
-    c->error = "grid too large: the traversal's visit counter has 25 bits";
+  if (c->nvox >= (1ull << 31) || vx_visibility_visits(c->geom) >= (1ull << 25) || c->geom.nx > 2047 || c->geom.ny > 2047 ||
+      c->geom.nz > 1023) {
+    c->error = "grid too large: the traversal packs positions into 11 + 11 + 10 bits and counts visits in 25 bits";
     return bail(VX_ERR_UNSUPPORTED);
   }
   c->words = (uint32_t)((c->nvox + 31) / 32);

@@ -277,14 +277,32 @@ __device__ __forceinline__ void prefix_walk(const Frame& f, const Wave& w, const
 // occludedBy() once per ray.  The loop body is the unit of work of the whole path, so the ray lives in
 // scalars: the same operations in the same order as VxRay (vx_dda.h), with the linear index kept
 // incrementally and the boundary tests of VoxelGrid.cpp:286-287,307 folded into one unsigned compare.
+// Position of a ray as one word: i | j << 11 | k << 22 (vx_create refuses grids beyond 2047 x 2047 x 1023).
+// A step is one add; a coordinate that leaves the grid on the low side wraps to the field's maximum (and
+// borrows from the next field), which the unsigned range test below reads as "outside", like a coordinate
+// that reaches the size.
+constexpr uint32_t kPosJ = 11, kPosK = 22, kPosMaskIJ = 0x7FFu;
+
+__device__ __forceinline__ bool coarse_set_packed(const Frame& f, const VisShared& sm, uint32_t P) {
+  if (f.cshift < 0) return true;
+  const uint32_t m = kPosMaskIJ >> f.cshift;
+  const uint32_t bi = (P >> f.cshift) & m, bj = (P >> (kPosJ + f.cshift)) & m, k = P >> kPosK;
+  const uint32_t C = (bi * (uint32_t)f.cyb + bj) * (uint32_t)f.g.nz + k;
+  return (sm.coarse[C >> 5] >> (C & 31u)) & 1u;
+}
+
 __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_t n_cast, uint32_t id_base, Stats& st) {
   const uint32_t lane = threadIdx.x & 31u;
   const int32_t normal = w.face == 0 ? 0 : 1;
   const uint32_t enc_epoch = f.epoch << kEpochShift;
   const int32_t stride_j = f.g.nz, stride_i = f.g.ny * f.g.nz;
+  const uint32_t nx1 = (uint32_t)f.g.nx - 1u, ny1 = (uint32_t)f.g.ny - 1u, nz1 = (uint32_t)f.g.nz - 1u;
+  // end voxel as a packed position; one that cannot be packed cannot be reached either
+  const bool end_in = (uint32_t)f.ex <= kPosMaskIJ && (uint32_t)f.ey <= kPosMaskIJ && (uint32_t)f.ez <= 0x3FFu;
+  const uint32_t pend = end_in ? ((uint32_t)f.ex | ((uint32_t)f.ey << kPosJ) | ((uint32_t)f.ez << kPosK)) : 0xFFFFFFFFu;
   bool active = false, exhausted = false, in_face = false, refill = true;
-  uint32_t rc = 0, id = 0, len = 0, L = 0;
-  int32_t i = 0, j = 0, k = 0, sx = 0, sy = 0, sz = 0;
+  uint32_t rc = 0, id = 0, len = 0, L = 0, P = 0;
+  int32_t dPx = 0, dPy = 0, dPz = 0, dLx = 0, dLy = 0, dLz = 0;
   float tx = 0.f, ty = 0.f, tz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
   for (;;) {
     if (refill) {  // warp-uniform: some lane ended its ray in the previous iteration (or this is the first one)
@@ -299,12 +317,20 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
           if (s < n_cast) {
             rc = sm.cand[s];
             id = id_base + s;
+            int32_t i, j, k;
             wave_cell(f, w, sm.rcell[rc], i, j, k);
             VxRay r0;
             ray_begin(f, sm, r0, i, j, k);
-            tx = r0.tx; dx = r0.dx; sx = r0.sx;
-            ty = r0.ty; dy = r0.dy; sy = r0.sy;
-            tz = r0.tz; dz = r0.dz; sz = r0.sz;
+            tx = r0.tx; dx = r0.dx;
+            ty = r0.ty; dy = r0.dy;
+            tz = r0.tz; dz = r0.dz;
+            dPx = r0.sx;
+            dPy = r0.sy * (1 << kPosJ);
+            dPz = r0.sz * (1 << kPosK);
+            dLx = r0.sx * stride_i;
+            dLy = r0.sy * stride_j;
+            dLz = r0.sz;
+            P = (uint32_t)i | ((uint32_t)j << kPosJ) | ((uint32_t)k << kPosK);
             L = lin(f.g, i, j, k);
             active = true;
             in_face = true;
@@ -320,50 +346,37 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
     }
     bool finished = false;
     if (active) {
-      // (i,j,k) = the current cell: inside the grid and free.  Which axis steps next (VoxelGrid.cpp:299-301):
-      // {2,1,2,1,2,2,0,0}[(tx<ty)<<2 | (tx<tz)<<1 | (ty<tz)]
+      // P = the current cell: inside the grid and free.  Which axis steps next (VoxelGrid.cpp:299-301):
+      // {2,1,2,1,2,2,0,0}[(tx<ty)<<2 | (tx<tz)<<1 | (ty<tz)].  Select-based: a warp running alone pays for
+      // every branch, and this loop is the critical path of a wave.
       const bool lt01 = tx < ty, lt02 = tx < tz, lt12 = ty < tz;
       const bool a0 = lt01 && lt02;
       const bool a1 = !lt01 && lt12;
+      const bool a01 = a0 || a1;
       const uint32_t Lc = L;
-      bool hit = false;
       if (in_face) {  // cells of this wave visited at or after the caster see this ray
-        const int32_t x = live_rank(f, w, sm, i, j, k);
+        const int32_t x = live_rank(f, w, sm, (int32_t)(P & kPosMaskIJ), (int32_t)((P >> kPosJ) & kPosMaskIJ), (int32_t)(P >> kPosK));
         if (x >= (int32_t)rc) atomicMax(&sm.owner[x], kSet | id);
-        if ((normal == 0 && a0) || (normal == 1 && a1)) in_face = false;
+        in_face = !(normal == 0 ? a0 : a1);
       }
       // step (VoxelGrid.cpp:304-305)
-      int32_t pos, size;
-      if (a0) {
-        i += sx;
-        tx = VX_FADD(tx, dx);
-        L += (uint32_t)(sx * stride_i);
-        pos = i;
-        size = f.g.nx;
-      } else if (a1) {
-        j += sy;
-        ty = VX_FADD(ty, dy);
-        L += (uint32_t)(sy * stride_j);
-        pos = j;
-        size = f.g.ny;
-      } else {
-        k += sz;
-        tz = VX_FADD(tz, dz);
-        L += (uint32_t)sz;
-        pos = k;
-        size = f.g.nz;
-      }
-      // leaves the grid (pos == Out after a positive step, pos <= 0 after a negative one: Out = 0 there and a
-      // step to -1 ends at the top of the reference loop), or reaches the end voxel: the ray misses
-      finished = (uint32_t)(pos - 1) >= (uint32_t)(size - 1) || (i == f.ex && j == f.ey && k == f.ez);
-      uint32_t word = 0;
-      const bool test = !finished && coarse_set(f, sm, i, j, k);
-      if (test) word = __ldg(f.occ + (L >> 5));  // in flight while the current cell is recorded
+      const float ntx = VX_FADD(tx, dx), nty = VX_FADD(ty, dy), ntz = VX_FADD(tz, dz);
+      tx = a0 ? ntx : tx;
+      ty = a1 ? nty : ty;
+      tz = a01 ? tz : ntz;
+      P += (uint32_t)(a0 ? dPx : (a1 ? dPy : dPz));
+      L += (uint32_t)(a0 ? dLx : (a1 ? dLy : dLz));
+      const uint32_t pos = a0 ? (P & kPosMaskIJ) : (a1 ? ((P >> kPosJ) & kPosMaskIJ) : (P >> kPosK));
+      const uint32_t lim = a0 ? nx1 : (a1 ? ny1 : nz1);
+      // leaves the grid (pos == Out after a positive step; 0 or wrapped after a negative one: Out = 0 there, and
+      // a step to -1 ends at the top of the reference loop), or reaches the end voxel: the ray misses
+      finished = (pos - 1u >= lim) | (P == pend);
       atomicMax(&f.memo[Lc], enc_epoch | id);
       ++len;
-      if (test && ((word >> (L & 31u)) & 1u)) {
-        finished = true;
-        hit = true;
+      bool hit = false;
+      if (!finished && coarse_set_packed(f, sm, P)) {  // ~5 % of the steps: the exact bit decides
+        hit = (__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u;
+        finished = hit;
       }
       if (finished) {
         if (hit) atomicOr(&f.hitbits[id >> 5], 1u << (id & 31u));
