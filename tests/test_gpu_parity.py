@@ -222,3 +222,36 @@ def test_more_passes_than_memo_epochs(orc, tmp_path):
     p = product_frame(be, poses, [0], [1, 2], extra_endpoints=eps)
     assert_frames_equal(p, o)
     be.close()
+
+
+def test_fill_groups_and_batches_do_not_change_a_byte(orc, tmp_path):
+    """The fill is organised by scan inside groups of `table_sets` frames and a call is cut into batches of
+    `frames_in_flight` frames: whatever the grouping, every frame must come out the same, and equal to the oracle."""
+    seq = make_sequence(str(tmp_path / "seq"), 14, 32, 500)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    cfg = vx.Config(cfg_path("example"))
+    specs, windows = [], []
+    for target in range(cnt):
+        pb, pe, qb, qe = vx.window(cnt, cfg.pod.priorScans, cfg.pod.pastScans, target)
+        prior, past = list(range(pb, pe)), list(range(qb, qe))
+        anchor = poses[prior[-1]]
+        ap_p, _ = vx.frame_transforms(anchor, np.stack([poses[i] for i in prior]))
+        ap_q, ep = vx.frame_transforms(anchor, np.stack([poses[i] for i in past]))
+        specs.append(vx.FrameSpec(np.asarray(prior, np.uint32), ap_p, np.asarray(past, np.uint32), ap_q, ep))
+        windows.append((prior, past))
+    results = []
+    for kw in (dict(), dict(table_sets=3), dict(table_sets=1, frames_in_flight=5), dict(table_sets=4, frames_in_flight=4)):
+        be = vx.Backend.from_config(cfg, **kw)
+        for t, (s, l) in enumerate(zip(scans, raw)):
+            be.upload_scan(t, s, l)
+        results.append(be.process(specs))
+        be.close()
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            for k in ("label", "bin", "occluded", "invalid"):
+                assert np.array_equal(a[k], b[k]), k
+    for f in (0, 6, cnt - 1):
+        o = oracle_frame(orc, cfg_path("example"), scans, labels, poses, *windows[f])
+        a = results[1][f]
+        assert np.array_equal(a["label"], o["label"]) and np.array_equal(a["bin"], o["bin"])
+        assert np.array_equal(a["occluded"], o["occluded_packed"]) and np.array_equal(a["invalid"], o["invalid_packed"])

@@ -391,7 +391,8 @@ class Backend:
     """One vx_ctx (one GPU)."""
 
     def __init__(self, resolution, min_extent, max_extent, min_range, max_range, hidecar=True, filtered=(), join_pairs=(),
-                 device: int = 0, frames_in_flight: int = 0, table_log2_capacity: int = 0, debug: bool = False, stream: int = 0):
+                 device: int = 0, frames_in_flight: int = 0, table_log2_capacity: int = 0, debug: bool = False, stream: int = 0,
+                 table_sets: int = 0):
         L = cuda_lib()
         gd = GridDesc(resolution=float(resolution))
         for a in range(3):
@@ -403,7 +404,7 @@ class Backend:
                         filtered_labels=self._filtered.ctypes.data if len(self._filtered) else None, n_filtered=len(self._filtered),
                         join_pairs=self._joins.ctypes.data if len(self._joins) else None, n_join_pairs=len(self._joins) // 2)
         op = Options(frames_in_flight=frames_in_flight, table_log2_capacity=table_log2_capacity, stream=stream or None,
-                     debug=1 if debug else 0)
+                     debug=1 if debug else 0, table_sets=table_sets)
         ctx = C.c_void_p()
         rc = L.vx_create(device, C.byref(gd), C.byref(fd), C.byref(op), C.byref(ctx))
         if rc != VX_OK:
