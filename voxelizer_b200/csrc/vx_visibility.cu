@@ -610,19 +610,35 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
     }
   }
 
-  // ---- D: apply the visit
-  for (uint32_t r = tid; r < n_live; r += kVisThreads) {
-    const uint32_t o = sm.owner[r];
-    const uint32_t id = o & kIdMask;
-    const bool hit = (o & kSet) && ((__ldcg(f.hitbits + (id >> 5)) >> (id & 31u)) & 1u);
-    int32_t i, j, k;
-    wave_cell(f, w, sm.rcell[r], i, j, k);
-    const uint32_t L = lin(f.g, i, j, k);
-    if (f.inv) {
-      if (!hit) atomicAnd(&f.live[L >> 5], ~(1u << (L & 31u)));  // invalid_ = -1, for good
-    } else {
-      if (hit) atomicOr(&f.occl[L >> 5], 1u << (L & 31u));       // last visit wins
-      else atomicAnd(&f.occl[L >> 5], ~(1u << (L & 31u)));
+  // ---- D: apply the visit.  All hit-bit gathers of a thread are in flight together (they were one
+  // dependent L2 / DRAM round trip per cell before).
+  {
+    uint32_t own[kLivePerThread], hw[kLivePerThread];
+#pragma unroll
+    for (int u = 0; u < kLivePerThread; ++u) {
+      const uint32_t r = tid + (uint32_t)u * kVisThreads;
+      own[u] = 0;
+      hw[u] = 0;
+      if (r < n_live) {
+        own[u] = sm.owner[r];
+        if (own[u] & kSet) hw[u] = __ldcg(f.hitbits + ((own[u] & kIdMask) >> 5));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kLivePerThread; ++u) {
+      const uint32_t r = tid + (uint32_t)u * kVisThreads;
+      if (r >= n_live) break;
+      const bool hit = (own[u] & kSet) && ((hw[u] >> (own[u] & 31u)) & 1u);
+      if (f.inv && hit) continue;  // the common case: still occluded from this endpoint, nothing to do
+      int32_t i, j, k;
+      wave_cell(f, w, sm.rcell[r], i, j, k);
+      const uint32_t L = lin(f.g, i, j, k);
+      if (f.inv) {
+        atomicAnd(&f.live[L >> 5], ~(1u << (L & 31u)));  // invalid_ = -1, for good
+      } else {
+        if (hit) atomicOr(&f.occl[L >> 5], 1u << (L & 31u));  // last visit wins
+        else atomicAnd(&f.occl[L >> 5], ~(1u << (L & 31u)));
+      }
     }
   }
   __syncthreads();
