@@ -81,4 +81,14 @@ struct VxVisFrame {
 
 __device__ __forceinline__ uint32_t vx_ldcg_u32(const uint32_t* p) { return __ldcg(p); }
 
+// Fire-and-forget reductions (SASS REDG).  Written in PTX because the compiler turns a result-less atomicXxx()
+// inside divergent code into the returning form (ATOM ..., RZ), which the warp then waits for.
+__device__ __forceinline__ void vx_red_add(uint32_t* p, uint32_t v) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v)); }
+__device__ __forceinline__ void vx_red_max(uint32_t* p, uint32_t v) { asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v)); }
+__device__ __forceinline__ void vx_red_or(uint32_t* p, uint32_t v) { asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v)); }
+__device__ __forceinline__ void vx_red_and(uint32_t* p, uint32_t v) { asm volatile("red.relaxed.gpu.global.and.b32 [%0], %1;" ::"l"(p), "r"(v)); }
+__device__ __forceinline__ void vx_red_max64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v));
+}
+
 #endif

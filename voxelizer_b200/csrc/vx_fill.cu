@@ -54,7 +54,7 @@ __device__ __forceinline__ void table_add(unsigned long long* keys, uint32_t* co
       if (seen == 0ull) seen = key1;
     }
     if (seen == key1) {
-      atomicAdd(&counts[h], n);
+      vx_red_add(&counts[h], n);
       return;
     }
     h = (h + 1u) & mask;
@@ -75,7 +75,7 @@ struct FillUse {  // one frame a scan goes into, staged in shared memory
   uint32_t both, pad;
 };
 
-__global__ void __launch_bounds__(kFillThreads)
+__global__ void __launch_bounds__(kFillThreads, 4)
 vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict__ uses, const float* __restrict__ ap_all,
                const VxSlot* __restrict__ slots, const VxGridGeom g, const VxFilterDev f) {
   __shared__ FillUse su[kFillUsesPerChunk];
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) vx_vote_kernel(const VxSlot* __restrict__
     for (int u = 0; u < kScanBatch; ++u) {
       if (k1[u] == 0ull) continue;
       const unsigned long long key = k1[u] - 1ull;
-      atomicMax(&t.best[key >> 16], ((unsigned long long)c[u] << 16) | (0xFFFFull - (key & 0xFFFFull)));
+      vx_red_max64(&t.best[key >> 16], ((unsigned long long)c[u] << 16) | (0xFFFFull - (key & 0xFFFFull)));
     }
   }
 }
@@ -287,10 +287,10 @@ __global__ void __launch_bounds__(256) vx_emit_kernel(const VxSlot* __restrict__
       t.best[L] = 0ull;
       if (is_target) {
         s.out_label[L] = (uint16_t)label;
-        atomicOr(&s.occ[L >> 5], 1u << (L & 31u));  // occupied = count > 0, whatever the label (VoxelGrid.cpp:45-63)
+        vx_red_or(&s.occ[L >> 5], 1u << (L & 31u));  // occupied = count > 0, whatever the label (VoxelGrid.cpp:45-63)
       } else if (label > 0u) {
         const uint32_t bb = L & 31u;
-        atomicOr(&s.out_bin[L >> 5], 1u << ((bb & 24u) | (7u - (bb & 7u))));  // element 8n + e -> byte n, bit 7 - e
+        vx_red_or(&s.out_bin[L >> 5], 1u << ((bb & 24u) | (7u - (bb & 7u))));  // element 8n + e -> byte n, bit 7 - e
       }
     }
   }

@@ -117,12 +117,6 @@ __device__ __forceinline__ uint32_t extract_bits(const uint32_t* bits, uint32_t 
   return len >= 32u ? v : (v & ((1u << len) - 1u));
 }
 
-// Fire-and-forget reductions (SASS REDG).  Written in PTX because the compiler turns a result-less atomicMax
-// in these divergent loops into the returning form (ATOM ..., RZ), which the warp then waits on.
-__device__ __forceinline__ void red_max(uint32_t* p, uint32_t v) { asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void red_or(uint32_t* p, uint32_t v) { asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void red_and(uint32_t* p, uint32_t v) { asm volatile("red.relaxed.gpu.global.and.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
 // exclusive prefix sum of one value per thread over the CTA; total in sm.scan_total (valid after return)
 __device__ __forceinline__ uint32_t block_scan(VisShared& sm, uint32_t v) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -377,7 +371,7 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
       // leaves the grid (pos == Out after a positive step; 0 or wrapped after a negative one: Out = 0 there, and
       // a step to -1 ends at the top of the reference loop), or reaches the end voxel: the ray misses
       finished = (pos - 1u >= lim) | (P == pend);
-      red_max(&f.memo[Lc], enc_epoch | id);
+      vx_red_max(&f.memo[Lc], enc_epoch | id);
       ++len;
       bool hit = false;
       if (!finished && coarse_set_packed(f, sm, P)) {  // ~5 % of the steps: the exact bit decides
@@ -385,7 +379,7 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
         finished = hit;
       }
       if (finished) {
-        if (hit) red_or(&f.hitbits[id >> 5], 1u << (id & 31u));
+        if (hit) vx_red_or(&f.hitbits[id >> 5], 1u << (id & 31u));
         st.steps += len;
         active = false;
       }
@@ -640,10 +634,10 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       wave_cell(f, w, sm.rcell[r], i, j, k);
       const uint32_t L = lin(f.g, i, j, k);
       if (f.inv) {
-        red_and(&f.live[L >> 5], ~(1u << (L & 31u)));  // invalid_ = -1, for good
+        vx_red_and(&f.live[L >> 5], ~(1u << (L & 31u)));  // invalid_ = -1, for good
       } else {
-        if (hit) red_or(&f.occl[L >> 5], 1u << (L & 31u));  // last visit wins
-        else red_and(&f.occl[L >> 5], ~(1u << (L & 31u)));
+        if (hit) vx_red_or(&f.occl[L >> 5], 1u << (L & 31u));  // last visit wins
+        else vx_red_and(&f.occl[L >> 5], ~(1u << (L & 31u)));
       }
     }
   }
