@@ -123,9 +123,8 @@ typedef struct vx_stage_times {
   uint64_t rays_cast; /* occludedBy calls (all passes) */
   uint64_t dda_steps; /* cells traversed by those rays */
   /* K4 anatomy, summed over frames: waves run, waves that needed the in-wave resolution, resolution
-   * sweeps, and SM cycles as seen by thread 0: [0..3] per phase (snapshot, resolve, trace, apply),
-   * [4] ray set-up inside trace, [5] trace loop iterations of warp 0 (a count, not cycles),
-   * [6] waiting for the other tracing warps, [7] reserved. */
+   * sweeps, and SM cycles as seen by thread 0 of each frame's CTA: [0..3] per phase (snapshot, resolve,
+   * trace, apply); [4..7] reserved (zero). */
   uint64_t vis_waves;
   uint64_t vis_resolve_waves;
   uint64_t vis_rounds;

@@ -40,5 +40,4 @@ print("fill GB/s", 20 * st["points_read"] / (st["fill_ms"] / 1e3) / 1e9, " point
 cyc = np.array(st["vis_cycles"], float)
 print("per frame: rays %.0f steps %.0f waves %.0f resolve %.0f rounds %.0f" % tuple(st[k] / f for k in ("rays_cast", "dda_steps", "vis_waves", "vis_resolve_waves", "vis_rounds")))
 print("cycles per wave  A snapshot %.0f | B resolve %.0f | C trace %.0f | D apply %.0f | total %.0f" % (*(cyc[:4] / st["vis_waves"]), cyc[:4].sum() / st["vis_waves"]))
-print("  C anatomy per wave: setup %.0f cyc | warp-0 iterations %.1f | barrier wait %.0f cyc" % (cyc[4] / st["vis_waves"], cyc[5] / st["vis_waves"], cyc[6] / st["vis_waves"]))
 print("Gsteps/s", st["dda_steps"] / (st["visibility_ms"] / 1e3) / 1e9)
