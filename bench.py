@@ -193,6 +193,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: voxelizer_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO prints to stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- CPU baseline (rank 0, N=1 only): the reference arm as a subprocess, one step
