@@ -193,8 +193,20 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: voxelizer_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO prints to stdout; stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: NCCL prints its version banner there while the communicator is
+        # created (first collective), so fd 1 points at stderr until that has happened
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     # ---- CPU baseline (rank 0, N=1 only): the reference arm as a subprocess, one step
     cpu_baseline = None
