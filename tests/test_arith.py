@@ -35,8 +35,8 @@ def floor_div(v, res):
     q0 = (v * rcp).astype(F)
     n = np.floor(q0)
     d = (q0 - n).astype(F)
-    margin = (np.abs(q0) * F(4.76837158e-7)).astype(F)
-    fast = (d > margin) & ((F(1.0) - d).astype(F) > margin)
+    with np.errstate(invalid="ignore"):
+        fast = np.abs((d - F(0.5)).astype(F)) < (F(0.5) - (np.abs(q0) * F(4.76837158e-7)).astype(F)).astype(F)  # floor_div3
     exact = np.floor((v / res).astype(F))
     return np.where(fast, n, exact), fast, exact
 

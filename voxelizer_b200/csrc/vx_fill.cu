@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int kFillThreads = 256;
-constexpr int kFillPointsPerThread = 4;
+constexpr int kFillPointsPerThread = 2;
 constexpr int kFillTile = kFillThreads * kFillPointsPerThread;
 constexpr int kFillUsesPerChunk = 16;  // frames staged in shared memory at a time
 
@@ -30,17 +30,24 @@ __device__ __forceinline__ uint32_t hash_slot(unsigned long long key1, uint32_t 
   return ((hi * 0x9E3779B1u) ^ (lo * 0x85EBCA77u)) >> (32u - log2_cap);
 }
 
-// floorf(__fdiv_rn(v, res)) without the division in the common case.  q0 = v * rcp (rcp = RN(1/res)) is
-// within 1.5 * 2^-23 relative of the correctly rounded quotient, so when q0 is further than 2^-21 |q0|
-// from both neighbouring integers the two have the same floor; otherwise (about 1 point in 10^4), and for
-// NaN / infinity, the IEEE division decides.
-__device__ __forceinline__ float floor_div(float v, float res, float rcp) {
-  const float q0 = __fmul_rn(v, rcp);
-  const float n = floorf(q0);
-  const float d = q0 - n;                            // exact: q0 and n share the exponent range
-  const float margin = fabsf(q0) * 4.76837158e-7f;   // 2^-21 |q0|
-  if (d > margin && (1.0f - d) > margin) return n;
-  return floorf(__fdiv_rn(v, res));
+// floorf(__fdiv_rn(v, res)) for the three coordinates without the divisions in the common case.  q = v * rcp
+// (rcp = RN(1/res)) is within 1.5 * 2^-23 relative of the correctly rounded quotient, so when q is further than
+// 2^-21 |q| from both neighbouring integers the two have the same floor; otherwise (about 1 point in 10^4), and
+// for NaN / infinity (every comparison false), the IEEE divisions decide.
+__device__ __forceinline__ void floor_div3(float vx, float vy, float vz, float res, float rcp, float& fx, float& fy, float& fz) {
+  const float qx = __fmul_rn(vx, rcp), qy = __fmul_rn(vy, rcp), qz = __fmul_rn(vz, rcp);
+  fx = floorf(qx);
+  fy = floorf(qy);
+  fz = floorf(qz);
+  // |d - 0.5| < 0.5 - margin  <=>  d > margin and 1 - d > margin, with d = q - floor(q) in [0, 1) (exact)
+  const float kMargin = 4.76837158e-7f;  // 2^-21
+  const bool safe = fabsf((qx - fx) - 0.5f) < 0.5f - fabsf(qx) * kMargin && fabsf((qy - fy) - 0.5f) < 0.5f - fabsf(qy) * kMargin &&
+                    fabsf((qz - fz) - 0.5f) < 0.5f - fabsf(qz) * kMargin;
+  if (!safe) {  // about 1 point in 10^4, and every NaN / infinity: the IEEE divisions decide
+    fx = floorf(__fdiv_rn(vx, res));
+    fy = floorf(__fdiv_rn(vy, res));
+    fz = floorf(__fdiv_rn(vz, res));
+  }
 }
 
 // (voxel,label) -> count.  `seen` = the slot's key as loaded earlier by the caller (possibly stale: a
@@ -75,7 +82,7 @@ struct FillUse {  // one frame a scan goes into, staged in shared memory
   uint32_t both, pad;
 };
 
-__global__ void __launch_bounds__(kFillThreads, 4)
+__global__ void __launch_bounds__(kFillThreads, 8)
 vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict__ uses, const float* __restrict__ ap_all,
                const VxSlot* __restrict__ slots, const VxGridGeom g, const VxFilterDev f) {
   __shared__ FillUse su[kFillUsesPerChunk];
@@ -164,9 +171,8 @@ vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict
         const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, x), __fmul_rn(m11, y)), __fmul_rn(m12, z)), m13);
         const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, x), __fmul_rn(m21, y)), __fmul_rn(m22, z)), m23);
         // VoxelGrid.cpp:46-53  floor((p - offset) / resolution), IEEE division; NaN / out of range rejected
-        const float fi = floor_div(__fsub_rn(tx, g.off[0]), g.res, rcp);
-        const float fj = floor_div(__fsub_rn(ty, g.off[1]), g.res, rcp);
-        const float fk = floor_div(__fsub_rn(tz, g.off[2]), g.res, rcp);
+        float fi, fj, fk;
+        floor_div3(__fsub_rn(tx, g.off[0]), __fsub_rn(ty, g.off[1]), __fsub_rn(tz, g.off[2]), g.res, rcp, fi, fj, fk);
         const bool in = ((keep0 >> u) & 1u) && (fi >= 0.0f) && (fi < fnx) && (fj >= 0.0f) && (fj < fny) && (fk >= 0.0f) && (fk < fnz);
         const uint32_t L = ((uint32_t)fi * (uint32_t)g.ny + (uint32_t)fj) * (uint32_t)g.nz + (uint32_t)fk;
         key1[u] = in ? ((((unsigned long long)L << 16) | (unsigned long long)lab[u]) + 1ull) : 0ull;
