@@ -79,13 +79,15 @@ struct FillUse {  // one frame a scan goes into, staged in shared memory
   uint32_t* counts_i;
   uint32_t* ovf_i;
   uint32_t log2_t, log2_i;
-  uint32_t both, pad;
+  uint32_t both;
+  uint32_t skip;  // the tile's bounding box, moved into this frame, lies clearly outside the grid
 };
 
 __global__ void __launch_bounds__(kFillThreads, 8)
 vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict__ uses, const float* __restrict__ ap_all,
                const VxSlot* __restrict__ slots, const VxGridGeom g, const VxFilterDev f) {
   __shared__ FillUse su[kFillUsesPerChunk];
+  __shared__ float bbox[kFillThreads / 32][6];  // per warp: min x,y,z, max x,y,z of the points that passed the filters
   const VxScanWork w = works[blockIdx.y];
   const uint32_t base = blockIdx.x * kFillTile;
   if (base >= w.n) return;
@@ -125,6 +127,31 @@ vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict
       if (!keep) keep0 &= ~(1u << u);
     }
   }
+  // bounding box of the surviving points (a frame whose grid the box cannot touch is skipped as a whole)
+  {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int u = 0; u < kFillPointsPerThread; ++u)
+      if ((keep0 >> u) & 1u) {
+        lo[0] = fminf(lo[0], px[u]); hi[0] = fmaxf(hi[0], px[u]);
+        lo[1] = fminf(lo[1], py[u]); hi[1] = fmaxf(hi[1], py[u]);
+        lo[2] = fminf(lo[2], pz[u]); hi[2] = fmaxf(hi[2], pz[u]);
+      }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], off));
+        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], off));
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        bbox[threadIdx.x >> 5][a] = lo[a];
+        bbox[threadIdx.x >> 5][3 + a] = hi[a];
+      }
+    }
+  }
   if (__syncthreads_or(keep0 != 0u) == 0) return;  // nothing of this tile survives the filters
 
   const float fnx = (float)g.nx, fny = (float)g.ny, fnz = (float)g.nz;
@@ -150,11 +177,37 @@ vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict
       d.ovf_i = s.input.overflow;
       d.log2_i = s.input.log2_cap;
       d.both = use.both;
+      // Where can the tile land in this frame?  centre' +- |R| * half-extent bounds every transformed point (NaN
+      // coordinates never enter fminf / fmaxf and are rejected per point anyway).  One metre of slack dwarfs any
+      // rounding difference between this bound and the per-point arithmetic.
+      float lo[3], hi[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = bbox[0][a];
+        hi[a] = bbox[0][3 + a];
+#pragma unroll
+        for (int wv = 1; wv < kFillThreads / 32; ++wv) {
+          lo[a] = fminf(lo[a], bbox[wv][a]);
+          hi[a] = fmaxf(hi[a], bbox[wv][3 + a]);
+        }
+      }
+      const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+      const float hx = 0.5f * (hi[0] - lo[0]), hy = 0.5f * (hi[1] - lo[1]), hz = 0.5f * (hi[2] - lo[2]);
+      const float gsize[3] = {(float)g.nx * g.res, (float)g.ny * g.res, (float)g.nz * g.res};
+      bool outside = false;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float centre = m[0 * 4 + r] * cx + m[1 * 4 + r] * cy + m[2 * 4 + r] * cz + m[3 * 4 + r];
+        const float reach = fabsf(m[0 * 4 + r]) * hx + fabsf(m[1 * 4 + r]) * hy + fabsf(m[2 * 4 + r]) * hz + 1.0f;
+        outside |= centre + reach < g.off[r] || centre - reach > g.off[r] + gsize[r];
+      }
+      d.skip = outside ? 1u : 0u;
     }
     __syncthreads();
 
     for (uint32_t q = 0; q < nq; ++q) {
       const FillUse& d = su[q];
+      if (d.skip) continue;
       const float m00 = d.m[0], m10 = d.m[1], m20 = d.m[2];
       const float m01 = d.m[3], m11 = d.m[4], m21 = d.m[5];
       const float m02 = d.m[6], m12 = d.m[7], m22 = d.m[8];
