@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) vx_clear_kernel(const VxSlot* __restrict_
   }
 }
 
-constexpr int kScanBatch = 8;  // histogram slots a thread has in flight (the scans are latency-bound otherwise)
+constexpr int kScanBatch = 16; // histogram slots a thread has in flight (the scans are latency-bound otherwise)
 
 // K3b.  best[L] = max over the labels of voxel L of (count << 16 | 0xFFFF - label): largest count, ties ->
 // smallest label -- the result of scanning the reference's std::map in ascending label order with a
