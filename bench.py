@@ -357,10 +357,10 @@ def run_ours(args):
             "stage_ms_per_step": {k: st[k] / args.steps for k in ("fill_ms", "vote_ms", "emit_ms", "visibility_ms", "pack_ms", "total_ms")},
             "roofline": {"bound": "hbm", "kernel": "vx_fill_kernel (K1+K2: transform, filter, key, histogram insert)",
                          "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak,
-                         # dram bytes per launch: the ncu --set full capture in profiles/ measured 0.116 x the algorithmic
+                         # dram bytes per launch: the ncu --set full capture in profiles/ measured 0.142 x the algorithmic
                          # bytes (a scan tile is loaded once and inserted into every frame of the launch that uses it)
-                         "traffic": 0.116 * fill_bytes / max(1, launches["fill_launches"]),
-                         "traffic_source": "profiles/r01_ncu_full_fill_v2.txt (dram__bytes_read+write / algorithmic bytes of that launch)",
+                         "traffic": 0.142 * fill_bytes / max(1, launches["fill_launches"]),
+                         "traffic_source": "profiles/r01_ncu_full_fill_final.txt (dram__bytes_read+write / algorithmic bytes of that launch)",
                          "peak_source": peak_src, "bytes_per_launch": fill_bytes / max(1, launches["fill_launches"]),
                          "ms_per_launch": st["fill_ms"] / max(1, launches["fill_launches"]),
                          "insert_vote_pack": {"achieved": ivp_bytes / ivp_s / 1e9 if ivp_s > 0 else 0.0,
