@@ -15,7 +15,8 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(PKG, "lib")
-CUDA_LIB = os.path.join(LIB_DIR, "libvoxelizer_b200.so")
+# developer switch for same-box A/B timing of two builds of the kernels (tools/dev_gpu_perf.py); never set in tests / bench
+CUDA_LIB = os.environ.get("VX_B200_CUDA_LIB") or os.path.join(LIB_DIR, "libvoxelizer_b200.so")
 HOST_LIB = os.path.join(LIB_DIR, "libvxhost.so")
 SYNTH_LIB = os.path.join(LIB_DIR, "libvxsynth.so")
 GEN_DATA_EXE = os.path.join(PKG, "bin", "vx_gen_data")

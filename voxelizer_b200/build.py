@@ -54,9 +54,10 @@ def _run(cmd: list[str], log: str | None = None) -> None:
         raise RuntimeError("build failed: " + " ".join(cmd))
 
 
-def build_cuda(force: bool = False) -> str:
+def build_cuda(force: bool = False, out: str | None = None) -> str:
     os.makedirs(LIB, exist_ok=True)
-    out = os.path.join(LIB, "libvoxelizer_b200.so")
+    out = out or os.path.join(LIB, "libvoxelizer_b200.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     cu = [os.path.join(CSRC, f) for f in ("vx_api.cu", "vx_fill.cu", "vx_visibility.cu")]
     deps = cu + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(ROOT, "include", "voxelizer_b200.h"))
