@@ -147,9 +147,10 @@ void vx_host_free(void* p);
 /* Device-resident scan cache (replaces KittiReader's pointsCache_/labelCache_, KittiReader.cpp:73-142).
  * xyzr: n x 4 float32 exactly as in a KITTI velodyne .bin (KittiReader.cpp:145-171); labels: n raw
  * uint32 words of the .label file -- the library applies the reader's "& 0xFFFF" (KittiReader.cpp:189).
- * The copy is enqueued on the context's stream: from pageable memory it has completed when the call
- * returns, from pinned memory (vx_host_alloc) it may still be in flight -- call vx_sync (or
- * vx_process_frames) before overwriting a pinned source buffer. */
+ * The copy is enqueued on an upload stream of the context: from pageable memory it has completed when the
+ * call returns, from pinned memory (vx_host_alloc) it may still be in flight -- vx_process_frames waits (on the
+ * device) for the scans its frames read and for nothing else, so frames can be voxelized while later scans
+ * are still arriving; call vx_sync before overwriting a pinned source buffer. */
 int vx_upload_scan(vx_ctx* ctx, uint32_t scan_id, const float* xyzr, const uint32_t* labels, uint32_t n);
 int vx_evict_scan(vx_ctx* ctx, uint32_t scan_id);
 int vx_evict_all(vx_ctx* ctx);

@@ -22,7 +22,18 @@ struct DeviceScan {
   float4* points = nullptr;
   uint32_t* labels = nullptr;
   uint32_t n = 0;
+  uint64_t seq = 0;  // upload sequence number (uploads run on their own stream, see UploadMark)
 };
+
+// Uploads are asynchronous on a copy stream of their own; every few of them an event is recorded there.  A
+// fill launch waits for the first mark at or after the newest scan it reads, so the first frames of a job are
+// voxelized while the rest of the sequence is still crossing PCIe.
+struct UploadMark {
+  uint64_t seq;
+  cudaEvent_t ev;
+};
+
+constexpr uint32_t kUploadsPerMark = 16;
 
 // Histogram + winner tables: shared by the frames of a batch that are `table_sets` apart.
 struct TableSet {
@@ -78,6 +89,13 @@ struct vx_ctx {
   uint32_t* d_counters = nullptr;  // max_slots * kCounterWords
   uint32_t* h_counters = nullptr;  // pinned mirror
   std::vector<cudaEvent_t> ev_sub;  // 4 per fill -> vote -> emit launch
+
+  // copy streams: uploads, and the outputs that are final before the traversal starts
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_copy_out = nullptr;
+  uint64_t upload_seq = 0, marked_seq = 0, done_seq = 0;
+  std::vector<UploadMark> marks;      // in upload order; completed ones are recycled
+  std::vector<cudaEvent_t> ev_pool;   // timing-less events
 
   // batch staging (items, ap, endpoints, vis frames): pinned host + device mirror
   unsigned char* h_stage = nullptr;
@@ -262,6 +280,45 @@ int ensure_stage(vx_ctx* c, size_t bytes) {
   return VX_OK;
 }
 
+int mark_uploads(vx_ctx* c) {
+  if (c->marked_seq == c->upload_seq) return VX_OK;
+  cudaEvent_t e = nullptr;
+  if (!c->ev_pool.empty()) {
+    e = c->ev_pool.back();
+    c->ev_pool.pop_back();
+  } else {
+    VX_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  VX_CUDA(c, cudaEventRecord(e, c->copy_in));
+  c->marks.push_back(UploadMark{c->upload_seq, e});
+  c->marked_seq = c->upload_seq;
+  return VX_OK;
+}
+
+void prune_marks(vx_ctx* c) {
+  size_t k = 0;
+  while (k < c->marks.size() && cudaEventQuery(c->marks[k].ev) == cudaSuccess) {
+    c->done_seq = c->marks[k].seq;
+    c->ev_pool.push_back(c->marks[k].ev);
+    ++k;
+  }
+  if (k) c->marks.erase(c->marks.begin(), c->marks.begin() + (long)k);
+  cudaGetLastError();  // cudaErrorNotReady of the query is not an error
+}
+
+// makes `st` wait until upload number `seq` has arrived; false if it already had
+int wait_for_upload(vx_ctx* c, cudaStream_t st, uint64_t seq, bool* waited) {
+  *waited = false;
+  if (seq <= c->done_seq) return VX_OK;
+  for (const UploadMark& m : c->marks)
+    if (m.seq >= seq) {
+      VX_CUDA(c, cudaStreamWaitEvent(st, m.ev, 0));
+      *waited = true;
+      return VX_OK;
+    }
+  return fail(c, VX_ERR_CUDA, "internal: upload without a mark");
+}
+
 // One batch of <= max_slots frames.  Returns VX_ERR_TABLE_OVERFLOW if a histogram table was too small
 // (caller grows the tables and retries).
 int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
@@ -299,6 +356,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   const uint32_t n_sub = (nb + c->table_sets - 1) / c->table_sets;
   std::vector<size_t> work_begin(n_sub + 1, 0);
   std::vector<uint32_t> sub_max_points(n_sub, 0);
+  std::vector<uint64_t> sub_need_seq(n_sub, 0);  // newest upload the group reads
   size_t wi = 0, ui = 0, ai = 0, ei = 0;
   uint64_t points = 0;
   std::vector<Use> group;
@@ -340,6 +398,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
       w.pad = 0;
       for (size_t q = k; q < k1; ++q) uses[ui++] = VxScanUse{group[q].slot, group[q].ap_index, group[q].both};
       if (w.n > sub_max_points[gi]) sub_max_points[gi] = w.n;
+      if (it->second.seq > sub_need_seq[gi]) sub_need_seq[gi] = it->second.seq;
       points += (uint64_t)w.n * (k1 - k);
       k = k1;
     }
@@ -360,6 +419,11 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   const float* d_ep = reinterpret_cast<const float*>(c->d_stage + off_ep);
   const VxVisFrame* d_vis = reinterpret_cast<const VxVisFrame*>(c->d_stage + off_vis);
 
+  // Uploads may still be in flight on the upload stream: each group waits for the newest scan it reads.
+  int rc2 = mark_uploads(c);
+  if (rc2 != VX_OK) return rc2;
+  prune_marks(c);
+
   // fill -> vote -> emit in groups of `table_sets` frames (frames of different groups share tables)
   while (c->ev_sub.size() < (size_t)n_sub * 4) {
     cudaEvent_t e;
@@ -367,10 +431,14 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     c->ev_sub.push_back(e);
   }
   uint64_t fill_launches = 0;
+  const uint32_t n_scratch = (uint32_t)c->scratch.size();
   VX_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], st));
   for (uint32_t g = 0; g < n_sub; ++g) {
     const uint32_t f0 = g * c->table_sets, f1 = f0 + c->table_sets < nb ? f0 + c->table_sets : nb;
     const uint32_t n_works = (uint32_t)(work_begin[g + 1] - work_begin[g]);
+    bool waited = false;
+    rc2 = wait_for_upload(c, st, sub_need_seq[g], &waited);
+    if (rc2 != VX_OK) return rc2;
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 0], st));
     VX_CUDA(c, vx_launch_fill(d_works + work_begin[g], n_works, sub_max_points[g], d_uses, d_ap, c->d_slots, c->geom, c->filter, st));
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 1], st));
@@ -380,20 +448,44 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 3], st));
     fill_launches += (n_works + 65534) / 65535;
   }
+  // ONE visibility launch per batch.  (Measured: a launch per group on streams of their own, started as soon as the
+  // group is filled, is slower -- every launch places its CTAs on the SMs in the same order, so 8 launches of 114
+  // CTAs load 114 SMs with 7 CTAs and leave 34 idle; with groups of 148 it still lost 6 % to the single launch.)
   VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS_BEGIN], st));
-  VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, c->d_scratch, (uint32_t)c->scratch.size(), c->d_locks, st));
+  VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, c->d_scratch, n_scratch, c->d_locks, st));
   VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS], st));
   VX_CUDA(c, vx_launch_pack(c->d_slots, nb, c->nvox, st));
   VX_CUDA(c, cudaEventRecord(c->ev[EV_PACK], st));
 
+  // Copy-out.  Everything above is enqueued by now: a copy into pageable memory blocks the host, never the device.
+  // `.label` / `.bin` are final after a group's emit: they leave on the copy stream while the rays are traced.
   const size_t packed = (size_t)(c->nvox / 8);
+  bool any_early = false;
+  for (uint32_t g = 0; g < n_sub; ++g) {
+    const uint32_t f0 = g * c->table_sets, f1 = f0 + c->table_sets < nb ? f0 + c->table_sets : nb;
+    bool first = true;
+    for (uint32_t f = f0; f < f1; ++f) {
+      const vx_frame_desc& fr = frames[f];
+      if (!fr.out_label && !fr.out_bin) continue;
+      if (first) {
+        VX_CUDA(c, cudaStreamWaitEvent(c->copy_out, c->ev_sub[4 * g + 3], 0));
+        first = false;
+        any_early = true;
+      }
+      const VxSlot& s = c->slots[f].dev;
+      if (fr.out_label) VX_CUDA(c, cudaMemcpyAsync(fr.out_label, s.out_label, (size_t)c->nvox * 2, cudaMemcpyDeviceToHost, c->copy_out));
+      if (fr.out_bin) VX_CUDA(c, cudaMemcpyAsync(fr.out_bin, s.out_bin, packed, cudaMemcpyDeviceToHost, c->copy_out));
+    }
+  }
   for (uint32_t f = 0; f < nb; ++f) {
     const vx_frame_desc& fr = frames[f];
     const VxSlot& s = c->slots[f].dev;
-    if (fr.out_label) VX_CUDA(c, cudaMemcpyAsync(fr.out_label, s.out_label, (size_t)c->nvox * 2, cudaMemcpyDeviceToHost, st));
-    if (fr.out_bin) VX_CUDA(c, cudaMemcpyAsync(fr.out_bin, s.out_bin, packed, cudaMemcpyDeviceToHost, st));
     if (fr.out_occluded) VX_CUDA(c, cudaMemcpyAsync(fr.out_occluded, s.out_occluded, packed, cudaMemcpyDeviceToHost, st));
     if (fr.out_invalid) VX_CUDA(c, cudaMemcpyAsync(fr.out_invalid, s.out_invalid, packed, cudaMemcpyDeviceToHost, st));
+  }
+  if (any_early) {
+    VX_CUDA(c, cudaEventRecord(c->ev_copy_out, c->copy_out));
+    VX_CUDA(c, cudaStreamWaitEvent(st, c->ev_copy_out, 0));
   }
   VX_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, (size_t)nb * kCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   VX_CUDA(c, cudaEventRecord(c->ev[EV_END], st));
@@ -504,6 +596,9 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
     c->own_stream = true;
   }
   for (int i = 0; i < EV_COUNT; ++i) VX_CREATE_CUDA(cudaEventCreate(&c->ev[i]));
+  VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+  VX_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_copy_out, cudaEventDisableTiming));
   {  // scans live in the device's stream-ordered memory pool; keep freed blocks for the next upload
     cudaMemPool_t pool;
     VX_CREATE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -594,12 +689,18 @@ void vx_destroy(vx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_in) cudaStreamSynchronize(c->copy_in);
   free_slots(c);
   for (auto& kv : c->scans) {
-    if (kv.second.points) cudaFreeAsync(kv.second.points, c->stream);
-    if (kv.second.labels) cudaFreeAsync(kv.second.labels, c->stream);
+    if (kv.second.points) cudaFreeAsync(kv.second.points, c->copy_in);
+    if (kv.second.labels) cudaFreeAsync(kv.second.labels, c->copy_in);
   }
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_in) cudaStreamSynchronize(c->copy_in);
+  for (const UploadMark& m : c->marks) cudaEventDestroy(m.ev);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->ev_copy_out) cudaEventDestroy(c->ev_copy_out);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
   for (ScratchMem& m : c->scratch)
     if (m.arena) cudaFree(m.arena);
   if (c->d_scratch) cudaFree(c->d_scratch);
@@ -641,11 +742,18 @@ int vx_upload_scan(vx_ctx* c, uint32_t scan_id, const float* xyzr, const uint32_
   DeviceScan s;
   s.n = n;
   if (n) {
-    // stream-ordered pool allocation: no device-wide synchronisation per scan
-    VX_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&s.points), (size_t)n * sizeof(float4), c->stream));
-    VX_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&s.labels), (size_t)n * sizeof(uint32_t), c->stream));
-    VX_CUDA(c, cudaMemcpyAsync(s.points, xyzr, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-    VX_CUDA(c, cudaMemcpyAsync(s.labels, labels, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    // stream-ordered pool allocation on the upload stream: no device-wide synchronisation per scan.  No kernel
+    // is pending when this is called (vx_process_frames returns after its batch), so blocks freed by an evict
+    // can be handed out again at once.
+    VX_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&s.points), (size_t)n * sizeof(float4), c->copy_in));
+    VX_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&s.labels), (size_t)n * sizeof(uint32_t), c->copy_in));
+    VX_CUDA(c, cudaMemcpyAsync(s.points, xyzr, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->copy_in));
+    VX_CUDA(c, cudaMemcpyAsync(s.labels, labels, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_in));
+    s.seq = ++c->upload_seq;
+    if (c->upload_seq - c->marked_seq >= kUploadsPerMark) {
+      const int rc = mark_uploads(c);
+      if (rc != VX_OK) return rc;
+    }
   }
   c->scans[scan_id] = s;
   return VX_OK;
@@ -655,8 +763,8 @@ int vx_evict_scan(vx_ctx* c, uint32_t scan_id) {
   if (!c) return VX_ERR_INVALID;
   const auto it = c->scans.find(scan_id);
   if (it == c->scans.end()) return VX_OK;
-  if (it->second.points) cudaFreeAsync(it->second.points, c->stream);
-  if (it->second.labels) cudaFreeAsync(it->second.labels, c->stream);
+  if (it->second.points) cudaFreeAsync(it->second.points, c->copy_in);
+  if (it->second.labels) cudaFreeAsync(it->second.labels, c->copy_in);
   c->scans.erase(it);
   return VX_OK;
 }
@@ -664,8 +772,8 @@ int vx_evict_scan(vx_ctx* c, uint32_t scan_id) {
 int vx_evict_all(vx_ctx* c) {
   if (!c) return VX_ERR_INVALID;
   for (auto& kv : c->scans) {
-    if (kv.second.points) cudaFreeAsync(kv.second.points, c->stream);
-    if (kv.second.labels) cudaFreeAsync(kv.second.labels, c->stream);
+    if (kv.second.points) cudaFreeAsync(kv.second.points, c->copy_in);
+    if (kv.second.labels) cudaFreeAsync(kv.second.labels, c->copy_in);
   }
   c->scans.clear();
   return VX_OK;
@@ -702,7 +810,9 @@ int vx_process_frames(vx_ctx* c, const vx_frame_desc* frames, uint32_t n) {
 int vx_sync(vx_ctx* c) {
   if (!c) return VX_ERR_INVALID;
   VX_CUDA(c, cudaSetDevice(c->device));
+  VX_CUDA(c, cudaStreamSynchronize(c->copy_in));
   VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  prune_marks(c);
   return VX_OK;
 }
 
