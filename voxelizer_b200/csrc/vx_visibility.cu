@@ -661,6 +661,8 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
   const uint32_t nvox = (uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz;
   const uint32_t words = (nvox + 31u) >> 5;
 
+  unsigned long long t_begin = 0;
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
   // claim a scratch buffer: at most as many CTAs are resident as there are buffers, so one is free
   if (tid == 0) {
     uint32_t s = blockIdx.x % n_scratch;
@@ -758,7 +760,15 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     const uint32_t used_words = min(hit_words, (id_base + 31u) >> 5);
     for (uint32_t x = tid; x < used_words; x += kVisThreads) f.hitbits[x] = 0;
     if (pass == 0) {  // invalid_ = occlusions_ (VoxelGrid.cpp:169): what is not occluded is dead from here on
-      for (uint32_t x = tid; x < words; x += kVisThreads) f.live[x] = __ldcg(f.occl + x) & ~__ldg(f.occ + x);
+      uint32_t n_live0 = 0, n_occ = 0;
+      for (uint32_t x = tid; x < words; x += kVisThreads) {
+        const uint32_t o = __ldg(f.occ + x);
+        const uint32_t l = __ldcg(f.occl + x) & ~o;
+        f.live[x] = l;
+        n_live0 += (uint32_t)__popc(l);
+        n_occ += (uint32_t)__popc(o);
+      }
+      atomicAdd(&slot.counters[12], (unsigned long long)n_live0 | ((unsigned long long)n_occ << 32));  // (statistics)
     }
     __syncthreads();
   }
@@ -781,6 +791,14 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     slot.counters[3] = st.resolve_waves;
     slot.counters[4] = st.rounds;
     for (int k = 0; k < 4; ++k) slot.counters[5 + k] = st.cyc[k];
+    // where and when the frame ran (developer statistics: VX_B200_FRAME_STATS)
+    uint32_t smid;
+    unsigned long long t_end;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    slot.counters[9] = smid;
+    slot.counters[10] = t_begin;
+    slot.counters[11] = t_end;
   }
 }
 
