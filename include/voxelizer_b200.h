@@ -152,6 +152,10 @@ void vx_host_free(void* p);
  * device) for the scans its frames read and for nothing else, so frames can be voxelized while later scans
  * are still arriving; call vx_sync before overwriting a pinned source buffer. */
 int vx_upload_scan(vx_ctx* ctx, uint32_t scan_id, const float* xyzr, const uint32_t* labels, uint32_t n);
+/* Completion of uploads, for callers that recycle a small pinned staging ring: vx_upload_ticket returns the number
+ * of uploads enqueued so far, vx_upload_wait blocks until that many have arrived on the device. */
+uint64_t vx_upload_ticket(const vx_ctx* ctx);
+int vx_upload_wait(vx_ctx* ctx, uint64_t ticket);
 int vx_evict_scan(vx_ctx* ctx, uint32_t scan_id);
 int vx_evict_all(vx_ctx* ctx);
 

@@ -24,7 +24,8 @@ GEN_DATA_EXE = os.path.join(PKG, "bin", "vx_gen_data")
 # every symbol include/voxelizer_b200.h declares
 C_ABI_SYMBOLS = (
     "vx_last_global_error", "vx_last_error", "vx_device_count", "vx_create", "vx_destroy", "vx_grid_info_get",
-    "vx_frames_in_flight", "vx_host_alloc", "vx_host_free", "vx_upload_scan", "vx_evict_scan", "vx_evict_all",
+    "vx_frames_in_flight", "vx_host_alloc", "vx_host_free", "vx_upload_scan", "vx_upload_ticket", "vx_upload_wait",
+    "vx_evict_scan", "vx_evict_all",
     "vx_process_frames", "vx_sync", "vx_stage_times_get", "vx_stage_times_reset", "vx_debug_dump",
 )
 
@@ -136,6 +137,9 @@ def cuda_lib():
         L.vx_host_alloc.argtypes = [C.c_size_t]
         L.vx_host_free.argtypes = [C.c_void_p]
         L.vx_upload_scan.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.vx_upload_ticket.restype = C.c_uint64
+        L.vx_upload_ticket.argtypes = [C.c_void_p]
+        L.vx_upload_wait.argtypes = [C.c_void_p, C.c_uint64]
         L.vx_evict_scan.argtypes = [C.c_void_p, C.c_uint32]
         L.vx_evict_all.argtypes = [C.c_void_p]
         L.vx_process_frames.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_uint32]

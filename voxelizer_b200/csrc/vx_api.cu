@@ -38,18 +38,15 @@ constexpr uint32_t kUploadsPerMark = 16;
 
 // Histogram + winner tables: shared by the frames of a batch that are `table_sets` apart.
 struct TableSet {
-  void* arena = nullptr;
   VxTable input{}, target{};
 };
 
 // Per-frame state that outlives fill -> vote -> emit: bitmaps and the four output images.
 struct FrameRec {
-  void* arena = nullptr;
   VxSlot dev{};  // device pointers (tables filled in from the frame's table set)
 };
 
 struct ScratchMem {
-  void* arena = nullptr;
   VxVisScratch dev{};
 };
 
@@ -84,6 +81,7 @@ struct vx_ctx {
   std::vector<TableSet> tables;
   std::vector<FrameRec> slots;
   std::vector<ScratchMem> scratch;  // one per resident visibility CTA
+  std::vector<void*> slot_slabs, scratch_slabs;  // one cudaMalloc per growth step, carved into the records above
   VxVisScratch* d_scratch = nullptr;
   uint32_t* d_locks = nullptr;
   VxSlot* d_slots = nullptr;
@@ -165,10 +163,8 @@ struct Carver {
   }
 };
 
-int alloc_table_set(vx_ctx* c, TableSet& t) {
-  const size_t bytes = table_set_bytes(c);
-  VX_CUDA(c, cudaMalloc(&t.arena, bytes));
-  Carver cv{static_cast<unsigned char*>(t.arena)};
+void carve_table_set(vx_ctx* c, TableSet& t, unsigned char* arena) {
+  Carver cv{arena};
   auto carve = [&](VxTable& tb, uint32_t log2_cap) {
     const size_t cap = (size_t)1 << log2_cap;
     tb.keys = reinterpret_cast<unsigned long long*>(cv.take(cap * 8));
@@ -178,14 +174,11 @@ int alloc_table_set(vx_ctx* c, TableSet& t) {
   };
   carve(t.target, c->log2_target);
   carve(t.input, c->log2_input);
-  VX_CUDA(c, cudaMemsetAsync(t.arena, 0, bytes, c->stream));  // all-zero = empty (vote / emit leave them empty again)
-  return VX_OK;
 }
 
-int alloc_frame(vx_ctx* c, uint32_t index) {
+void carve_frame(vx_ctx* c, uint32_t index, unsigned char* arena) {
   FrameRec& s = c->slots[index];
-  VX_CUDA(c, cudaMalloc(&s.arena, frame_bytes(c)));
-  Carver cv{static_cast<unsigned char*>(s.arena)};
+  Carver cv{arena};
   const TableSet& t = c->tables[index % c->table_sets];
   uint32_t* cnt = c->d_counters + (size_t)index * kCounterWords;
   s.dev.target = t.target;
@@ -200,39 +193,35 @@ int alloc_frame(vx_ctx* c, uint32_t index) {
   s.dev.out_bin = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
   s.dev.out_occluded = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
   s.dev.out_invalid = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
-  return VX_OK;
 }
 
 void free_slots(vx_ctx* c) {
-  for (FrameRec& s : c->slots)
-    if (s.arena) cudaFree(s.arena);
+  for (void* p : c->slot_slabs) cudaFree(p);
+  c->slot_slabs.clear();
   c->slots.clear();
-  for (TableSet& t : c->tables)
-    if (t.arena) cudaFree(t.arena);
   c->tables.clear();
   c->tables_dirty = false;
 }
 
+// One cudaMalloc per growth step (a whole sequence needs ~900 frame records: one call, not 900).
 int ensure_slots(vx_ctx* c, uint32_t n) {
   const uint32_t want_sets = n < c->table_sets ? n : c->table_sets;
-  while (c->tables.size() < want_sets) {
-    c->tables.emplace_back();
-    const int rc = alloc_table_set(c, c->tables.back());
-    if (rc != VX_OK) {
-      c->tables.pop_back();
-      return rc;
-    }
+  if (c->tables.size() < want_sets) {
+    const size_t old = c->tables.size(), add = want_sets - old, each = table_set_bytes(c);
+    void* slab = nullptr;
+    VX_CUDA(c, cudaMalloc(&slab, add * each));
+    c->slot_slabs.push_back(slab);
+    VX_CUDA(c, cudaMemsetAsync(slab, 0, add * each, c->stream));  // all-zero = empty (vote / emit leave them empty again)
+    c->tables.resize(want_sets);
+    for (size_t i = 0; i < add; ++i) carve_table_set(c, c->tables[old + i], static_cast<unsigned char*>(slab) + i * each);
   }
   if (c->slots.size() >= n) return VX_OK;
-  const size_t old = c->slots.size();
+  const size_t old = c->slots.size(), add = n - old, each = frame_bytes(c);
+  void* slab = nullptr;
+  VX_CUDA(c, cudaMalloc(&slab, add * each));
+  c->slot_slabs.push_back(slab);
   c->slots.resize(n);
-  for (size_t i = old; i < n; ++i) {
-    const int rc = alloc_frame(c, (uint32_t)i);
-    if (rc != VX_OK) {
-      c->slots.resize(i);
-      return rc;
-    }
-  }
+  for (size_t i = 0; i < add; ++i) carve_frame(c, (uint32_t)(old + i), static_cast<unsigned char*>(slab) + i * each);
   std::vector<VxSlot> host(n);
   for (size_t i = 0; i < n; ++i) host[i] = c->slots[i].dev;
   VX_CUDA(c, cudaMemcpyAsync(c->d_slots, host.data(), n * sizeof(VxSlot), cudaMemcpyHostToDevice, c->stream));
@@ -251,14 +240,15 @@ int ensure_scratch(vx_ctx* c, uint32_t n_frames) {
   }
   if (want > n_frames) want = n_frames;
   if (c->scratch.size() >= want) return VX_OK;
-  const size_t old = c->scratch.size();
+  const size_t old = c->scratch.size(), each = scratch_bytes(c);
+  void* slab = nullptr;
+  VX_CUDA(c, cudaMalloc(&slab, (want - old) * each));
+  c->scratch_slabs.push_back(slab);
   c->scratch.resize(want);
   for (size_t i = old; i < want; ++i) {
-    ScratchMem& m = c->scratch[i];
-    VX_CUDA(c, cudaMalloc(&m.arena, scratch_bytes(c)));
-    Carver cv{static_cast<unsigned char*>(m.arena)};
-    m.dev.memo = reinterpret_cast<uint32_t*>(cv.take(c->nvox * 4));
-    m.dev.hitbits = reinterpret_cast<uint32_t*>(cv.take((c->visits / 32 + 1) * 4));
+    Carver cv{static_cast<unsigned char*>(slab) + (i - old) * each};
+    c->scratch[i].dev.memo = reinterpret_cast<uint32_t*>(cv.take(c->nvox * 4));
+    c->scratch[i].dev.hitbits = reinterpret_cast<uint32_t*>(cv.take((c->visits / 32 + 1) * 4));
   }
   std::vector<VxVisScratch> host(want);
   for (size_t i = 0; i < want; ++i) host[i] = c->scratch[i].dev;
@@ -717,8 +707,7 @@ void vx_destroy(vx_ctx* c) {
   if (c->ev_copy_out) cudaEventDestroy(c->ev_copy_out);
   if (c->copy_out) cudaStreamDestroy(c->copy_out);
   if (c->copy_in) cudaStreamDestroy(c->copy_in);
-  for (ScratchMem& m : c->scratch)
-    if (m.arena) cudaFree(m.arena);
+  for (void* p : c->scratch_slabs) cudaFree(p);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_locks) cudaFree(c->d_locks);
   for (cudaEvent_t e : c->ev_sub) cudaEventDestroy(e);
@@ -772,6 +761,26 @@ int vx_upload_scan(vx_ctx* c, uint32_t scan_id, const float* xyzr, const uint32_
     }
   }
   c->scans[scan_id] = s;
+  return VX_OK;
+}
+
+uint64_t vx_upload_ticket(const vx_ctx* c) { return c ? c->upload_seq : 0; }
+
+int vx_upload_wait(vx_ctx* c, uint64_t ticket) {
+  if (!c) return VX_ERR_INVALID;
+  if (ticket > c->upload_seq) ticket = c->upload_seq;
+  if (ticket <= c->done_seq) return VX_OK;
+  VX_CUDA(c, cudaSetDevice(c->device));
+  if (ticket > c->marked_seq) {
+    const int rc = mark_uploads(c);
+    if (rc != VX_OK) return rc;
+  }
+  for (const UploadMark& m : c->marks)
+    if (m.seq >= ticket) {
+      VX_CUDA(c, cudaEventSynchronize(m.ev));
+      break;
+    }
+  prune_marks(c);
   return VX_OK;
 }
 

@@ -5,10 +5,14 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iostream>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -51,7 +55,10 @@ struct ResidentScan {
   uint32_t labelled = 0;  // labels > 0 after the 0xFFFF mask
 };
 
-// One pinned output set per frame of a batch.
+// One output set per frame of a batch, in PAGEABLE memory: pinning ~5 MB per frame costs seconds for a whole
+// sequence (more than reading it), while a device -> pageable copy only blocks this thread, which has nothing else
+// to do -- `.label` / `.bin` leave the device while the rays are traced (vx_api.cu: copy-out), the page faults of the
+// first touch included.
 struct OutputRing {
   uint8_t* base = nullptr;
   size_t perFrame = 0, labelBytes = 0, packedBytes = 0;
@@ -60,18 +67,149 @@ struct OutputRing {
     labelBytes = gi.label_bytes;
     packedBytes = gi.packed_bytes;
     perFrame = ((labelBytes + 3 * packedBytes + 255) / 256) * 256;
-    base = static_cast<uint8_t*>(vx_host_alloc(perFrame * n));
+    base = static_cast<uint8_t*>(std::malloc(perFrame * n));
     frames = n;
     return base != nullptr;
   }
   void release() {
-    if (base) vx_host_free(base);
+    std::free(base);
     base = nullptr;
   }
   uint16_t* label(uint32_t f) const { return reinterpret_cast<uint16_t*>(base + perFrame * f); }
   uint8_t* bin(uint32_t f) const { return base + perFrame * f + labelBytes; }
   uint8_t* occluded(uint32_t f) const { return bin(f) + packedBytes; }
   uint8_t* invalid(uint32_t f) const { return bin(f) + 2 * packedBytes; }
+};
+
+// Persistent worker threads for "parallel for" over file reads.
+class WorkerPool {
+ public:
+  explicit WorkerPool(int n) {
+    for (int i = 0; i < std::max(1, n); ++i) threads_.emplace_back([this]() { work(); });
+  }
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> lock(m_);
+      stop_ = true;
+    }
+    wake_.notify_all();
+    for (std::thread& t : threads_) t.join();
+  }
+  // fn(i) for i in [0, count); returns when all are done; the first exception is rethrown here
+  void run(size_t count, const std::function<void(size_t)>& fn) {
+    if (count == 0) return;
+    std::unique_lock<std::mutex> lock(m_);
+    fn_ = &fn;
+    count_ = count;
+    next_ = 0;
+    pending_ = count;
+    error_ = nullptr;
+    ++generation_;
+    wake_.notify_all();
+    done_.wait(lock, [this]() { return pending_ == 0; });
+    fn_ = nullptr;
+    if (error_) std::rethrow_exception(error_);
+  }
+
+ private:
+  void work() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lock(m_);
+    for (;;) {
+      wake_.wait(lock, [&]() { return stop_ || (generation_ != seen && next_ < count_); });
+      if (stop_) return;
+      while (next_ < count_) {
+        const size_t i = next_++;
+        const std::function<void(size_t)>* fn = fn_;
+        lock.unlock();
+        std::exception_ptr err;
+        try {
+          (*fn)(i);
+        } catch (...) {
+          err = std::current_exception();
+        }
+        lock.lock();
+        if (err && !error_) error_ = err;
+        if (--pending_ == 0) done_.notify_all();
+      }
+      seen = generation_;
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable wake_, done_;
+  const std::function<void(size_t)>* fn_ = nullptr;
+  size_t count_ = 0, next_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
+  std::exception_ptr error_;
+};
+
+// Disk -> pinned staging ring -> device.  The ring has two halves of kChunk slots: the workers read the files of
+// one chunk into one half while the uploads of the other half are in flight (vx_upload_ticket / vx_upload_wait).
+class ScanLoader {
+ public:
+  static constexpr uint32_t kChunk = 16;
+  ScanLoader(const KittiReader& reader, vx_ctx* ctx, int threads) : reader_(reader), ctx_(ctx), pool_(threads) {}
+  ~ScanLoader() {
+    if (ring_) vx_host_free(ring_);
+  }
+  // pinned staging ring with slots for the largest scan of the sequence (sizes from the directory, no file is opened)
+  bool prepare() {
+    uint64_t largest = 0;
+    for (uint32_t t = 0; t < reader_.count(); ++t) {
+      struct stat st;
+      if (::stat(reader_.velodyneFilename(t).c_str(), &st) == 0) largest = std::max<uint64_t>(largest, uint64_t(st.st_size));
+    }
+    capacity_ = uint32_t(largest / 16) + 1;
+    slotBytes_ = ((size_t(capacity_) * 20 + 255) / 256) * 256;
+    ring_ = static_cast<uint8_t*>(vx_host_alloc(slotBytes_ * 2 * kChunk));
+    return ring_ != nullptr;
+  }
+  // uploads the scans `todo` and records them in `resident`; throws std::runtime_error
+  void load(const std::vector<uint32_t>& todo, std::map<uint32_t, ResidentScan>& resident) {
+    if (todo.empty()) return;
+    uint64_t ticket[2] = {0, 0};
+    uint32_t points[kChunk], labelled[kChunk];
+    bool fits[kChunk];
+    for (size_t base = 0, turn = 0; base < todo.size(); base += kChunk, ++turn) {
+      const size_t n = std::min<size_t>(kChunk, todo.size() - base);
+      const size_t half = turn & 1;
+      if (turn >= 2 && vx_upload_wait(ctx_, ticket[half]) != VX_OK) throw std::runtime_error(vx_last_error(ctx_));
+      pool_.run(n, [&](size_t i) { fits[i] = reader_.loadInto(todo[base + i], xyzr(half, i), labels(half, i), capacity_, points[i], labelled[i]); });
+      for (size_t i = 0; i < n; ++i) {
+        const uint32_t t = todo[base + i];
+        ResidentScan r;
+        r.pose = reader_.pose(t);
+        if (fits[i]) {
+          r.points = points[i];
+          r.labelled = labelled[i];
+          if (vx_upload_scan(ctx_, t, xyzr(half, i), labels(half, i), r.points) != VX_OK) throw std::runtime_error(vx_last_error(ctx_));
+        } else {  // a file that grew since the ring was sized: the plain path
+          Laserscan scan;
+          std::vector<uint32_t> lab;
+          reader_.load(t, scan, lab);
+          r.points = scan.size();
+          for (const uint32_t l : lab) r.labelled += l > 0 ? 1u : 0u;
+          if (vx_upload_scan(ctx_, t, scan.xyzr.data(), lab.data(), r.points) != VX_OK) throw std::runtime_error(vx_last_error(ctx_));
+        }
+        resident[t] = r;
+      }
+      ticket[half] = vx_upload_ticket(ctx_);
+    }
+    // the ring may be reused (or freed) by the next call only after these uploads have landed
+    if (vx_upload_wait(ctx_, vx_upload_ticket(ctx_)) != VX_OK) throw std::runtime_error(vx_last_error(ctx_));
+  }
+
+ private:
+  float* xyzr(size_t half, size_t i) const { return reinterpret_cast<float*>(ring_ + slotBytes_ * (half * kChunk + i)); }
+  uint32_t* labels(size_t half, size_t i) const { return reinterpret_cast<uint32_t*>(ring_ + slotBytes_ * (half * kChunk + i) + size_t(capacity_) * 16); }
+  const KittiReader& reader_;
+  vx_ctx* ctx_;
+  WorkerPool pool_;
+  uint8_t* ring_ = nullptr;
+  size_t slotBytes_ = 0;
+  uint32_t capacity_ = 0;
 };
 
 }  // namespace
@@ -192,17 +330,17 @@ int runGenData(const Config& config, const std::string& sequenceDir, const std::
     writers.clear();
   };
   std::map<uint32_t, ResidentScan> resident;
+  ScanLoader loader(reader, ctx, std::max(1, opt.readThreads));
   int rc = 0;
   std::string err;
+  if (!targets.empty() && !loader.prepare()) {
+    rc = -1;
+    err = "pinned staging ring allocation failed";
+  }
 
   for (size_t base = 0, turn = 0; base < targets.size() && rc == 0; base += batch, ++turn) {
     const uint32_t nb = uint32_t(std::min<size_t>(batch, targets.size() - base));
     OutputRing& ring = rings[turn & 1];
-    if (opt.writeFiles && !ring.base && !ring.allocate(std::min<uint32_t>(batch, uint32_t(targets.size())), gi)) {
-      rc = -1;
-      err = "pinned output ring allocation failed";
-      break;
-    }
 
     // ---- residency: scans [lo, hi) of this batch; older ones are evicted
     int32_t lo = INT32_MAX, hi = 0;
@@ -221,24 +359,20 @@ int runGenData(const Config& config, const std::string& sequenceDir, const std::
         ++it;
       }
     }
+    std::vector<uint32_t> todo;
+    for (int32_t t = lo; t < hi; ++t)
+      if (!resident.count(uint32_t(t))) todo.push_back(uint32_t(t));
     try {
-      Laserscan scan;
-      std::vector<uint32_t> labels;
-      for (int32_t t = lo; t < hi; ++t) {
-        if (resident.count(uint32_t(t))) continue;
-        reader.load(uint32_t(t), scan, labels);
-        ResidentScan r;
-        r.pose = scan.pose;
-        r.points = scan.size();
-        for (const uint32_t l : labels) r.labelled += l > 0 ? 1u : 0u;
-        if (vx_upload_scan(ctx, uint32_t(t), scan.xyzr.data(), labels.data(), r.points) != VX_OK) throw std::runtime_error(vx_last_error(ctx));
-        resident[uint32_t(t)] = r;
-      }
+      loader.load(todo, resident);
     } catch (const std::exception& e) {
       rc = -1;
       err = e.what();
-      break;
     }
+    if (rc == 0 && opt.writeFiles && !ring.base && !ring.allocate(std::min<uint32_t>(batch, uint32_t(targets.size())), gi)) {
+      rc = -1;
+      err = "output ring allocation failed";
+    }
+    if (rc != 0) break;
     st.read_s += now() - t_read;
 
     // ---- frame descriptors

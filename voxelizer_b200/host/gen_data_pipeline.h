@@ -1,7 +1,8 @@
 // The gen_data frame loop (src/gen_data.cpp:19-145) re-organised for a GPU: the target list and the
 // windows are planned on the host exactly as the reference walks them, the frames are then pushed
 // through the C ABI (include/voxelizer_b200.h) in batches, and the four files per frame are written by
-// a small pool of writer threads while the next batch is on the device.
+// a small pool of writer threads while the next batch is on the device.  Scans are read by a pool of
+// reader threads through a small pinned staging ring; outputs land in pageable memory.
 #ifndef VOXELIZER_B200_HOST_GEN_DATA_PIPELINE_H_
 #define VOXELIZER_B200_HOST_GEN_DATA_PIPELINE_H_
 
@@ -24,7 +25,8 @@ struct GenDataOptions {
   int64_t maxFrames = -1;       // -1 = all
   bool writeFiles = true;
   bool verbose = true;
-  int ioThreads = 4;
+  int ioThreads = 8;    // file writers
+  int readThreads = 8;  // file readers (disk -> pinned staging ring -> device)
 };
 
 struct GenDataStats {

@@ -1,5 +1,9 @@
 #include "kitti_reader.h"
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <dirent.h>
 #include <sys/stat.h>
 
@@ -161,6 +165,50 @@ void KittiReader::load(uint32_t t, Laserscan& scan, std::vector<uint32_t>& label
     std::cout << "num. points = " << scan.size() << " vs. num. labels = " << labels.size() << std::endl;
     throw std::runtime_error("Inconsistent number of labels.");
   }
+}
+
+namespace {
+
+// whole file into `dst` (at most `capacity` bytes); returns the file size, or -1 if it cannot be opened
+int64_t slurp(const std::string& filename, void* dst, size_t capacity) {
+  const int fd = ::open(filename.c_str(), O_RDONLY);
+  if (fd < 0) return -1;
+  struct stat st;
+  if (::fstat(fd, &st) != 0) {
+    ::close(fd);
+    return -1;
+  }
+  const size_t want = std::min<size_t>(size_t(st.st_size), capacity);
+  size_t got = 0;
+  while (got < want) {
+    const ssize_t n = ::read(fd, static_cast<char*>(dst) + got, want - got);
+    if (n <= 0) break;
+    got += size_t(n);
+  }
+  ::close(fd);
+  return int64_t(st.st_size);
+}
+
+}  // namespace
+
+bool KittiReader::loadInto(uint32_t t, float* xyzr, uint32_t* labels, uint32_t capacity, uint32_t& points, uint32_t& labelled) const {
+  const int64_t pointBytes = slurp(velodyne_filenames_.at(t), xyzr, size_t(capacity) * 16);
+  const int64_t labelBytes = slurp(label_filenames_.at(t), labels, size_t(capacity) * 4);
+  const uint32_t np = pointBytes < 0 ? 0u : uint32_t(pointBytes / 16);  // unreadable = empty, as readPoints / readLabels
+  const uint32_t nl = labelBytes < 0 ? 0u : uint32_t(labelBytes / 4);
+  if (labelBytes < 0) std::cerr << "Unable to open label file. " << std::endl;
+  if (np != nl) {
+    std::cout << "Filename: " << velodyne_filenames_[t] << std::endl;
+    std::cout << "Filename: " << label_filenames_[t] << std::endl;
+    std::cout << "num. points = " << np << " vs. num. labels = " << nl << std::endl;
+    throw std::runtime_error("Inconsistent number of labels.");
+  }
+  if (np > capacity) return false;
+  points = np;
+  uint32_t count = 0;
+  for (uint32_t i = 0; i < np; ++i) count += (labels[i] & 0xFFFFu) > 0 ? 1u : 0u;
+  labelled = count;
+  return true;
 }
 
 void KittiReader::window(int32_t idx, int32_t& priorBegin, int32_t& priorEnd, int32_t& pastBegin, int32_t& pastEnd) const {

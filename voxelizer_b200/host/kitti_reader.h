@@ -68,6 +68,10 @@ class KittiReader {
   void window(int32_t idx, int32_t& priorBegin, int32_t& priorEnd, int32_t& pastBegin, int32_t& pastEnd) const;
   /** reads scan t from disk (no cache); throws like retrieve() on a label-count mismatch. */
   void load(uint32_t t, Laserscan& scan, std::vector<uint32_t>& labels) const;
+  /** the same straight into caller memory (e.g. a pinned staging slot of `capacity` points): raw labels (the
+   *  device applies & 0xFFFF), `labelled` = labels > 0 after the mask.  false if the scan does not fit. */
+  bool loadInto(uint32_t t, float* xyzr, uint32_t* labels, uint32_t capacity, uint32_t& points, uint32_t& labelled) const;
+  const Matrix4f& pose(uint32_t t) const { return poses_.at(t); }
   const std::string& velodyneFilename(uint32_t t) const { return velodyne_filenames_[t]; }
   void setVerbose(bool v) { verbose_ = v; }
 
