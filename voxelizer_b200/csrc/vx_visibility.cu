@@ -99,6 +99,7 @@ struct Frame {
   uint32_t* occl;
   float e0, e1, e2;
   int32_t ex, ey, ez;  // end voxel of the pass (VoxelGrid.h:99-102: truncation)
+  uint32_t pend;       // ... as a packed position; one that cannot be packed (outside the grid) cannot be reached either
   uint32_t epoch;
   bool inv;
   bool tables;        // sm.axis holds this pass's ray set-up
@@ -297,9 +298,7 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
   const uint32_t enc_epoch = f.epoch << kEpochShift;
   const int32_t stride_j = f.g.nz, stride_i = f.g.ny * f.g.nz;
   const uint32_t nx1 = (uint32_t)f.g.nx - 1u, ny1 = (uint32_t)f.g.ny - 1u, nz1 = (uint32_t)f.g.nz - 1u;
-  // end voxel as a packed position; one that cannot be packed cannot be reached either
-  const bool end_in = (uint32_t)f.ex <= kPosMaskIJ && (uint32_t)f.ey <= kPosMaskIJ && (uint32_t)f.ez <= 0x3FFu;
-  const uint32_t pend = end_in ? ((uint32_t)f.ex | ((uint32_t)f.ey << kPosJ) | ((uint32_t)f.ez << kPosK)) : 0xFFFFFFFFu;
+  const uint32_t pend = f.pend;
   bool active = false, exhausted = false, in_face = false, refill = true;
   uint32_t rc = 0, id = 0, len = 0, L = 0, P = 0;
   int32_t dPx = 0, dPy = 0, dPz = 0, dLx = 0, dLy = 0, dLz = 0;
@@ -738,6 +737,9 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     f.ex = vx_trunc_i32(VX_FDIV(VX_FSUB(f.e0, g.off[0]), g.res));
     f.ey = vx_trunc_i32(VX_FDIV(VX_FSUB(f.e1, g.off[1]), g.res));
     f.ez = vx_trunc_i32(VX_FDIV(VX_FSUB(f.e2, g.off[2]), g.res));
+    f.pend = ((uint32_t)f.ex <= kPosMaskIJ && (uint32_t)f.ey <= kPosMaskIJ && (uint32_t)f.ez <= 0x3FFu)
+                 ? ((uint32_t)f.ex | ((uint32_t)f.ey << 11) | ((uint32_t)f.ez << 22))
+                 : 0xFFFFFFFFu;
     f.epoch = (pass % kMaxEpoch) + 1u;
     build_axis_table(f, sm);  // (barrier inside)
     if (pass % kMaxEpoch == 0) {  // first pass, or the epoch counter restarts: forget every memo
