@@ -20,7 +20,7 @@
 //          crossed are CANDIDATES.
 //       B  which candidates cast?  c casts iff no CASTING candidate visited earlier crosses c with
 //          the in-face part of its ray (rays are monotone per axis: they never re-enter the face).
-//          Counters: cnt[c] = undecided earlier candidates crossing c.  killed -> no cast (releases
+//          Counters: cnt[c] = undecided earlier candidates crossing c (their crossed cells are remembered in registers).  killed -> no cast (releases
 //          its successors); cnt == 0 -> casts (kills its successors).  Monotone, so any thread
 //          interleaving gives the reference's answer; chains resolve in as many sweeps as they are long.
 //       C  casters get ray ids in visit order and trace: RED.MAX(memo[cell], id) = "latest ray wins";
@@ -516,7 +516,11 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   uint32_t n_cast = 0;
   if (n_cand > 0) {
     const int32_t normal = face == 0 ? 0 : 1;
-    // ---- B0: cnt[x] = candidates visited before x whose in-face ray crosses x
+    // ---- B0: cnt[x] = candidates visited before x whose in-face ray crosses x.  The crossed candidates of a thread's
+    // first candidate (most waves have <= 128) are remembered in a register, so that the sweeps below do not walk
+    // the ray again: up to eight live ranks, 16 bits each.
+    unsigned long long crossed = 0, crossed_hi = 0;
+    uint32_t n_crossed = 0;  // > 8: more than fit, walk again
     for (uint32_t p = tid; p < n_cand; p += kVisThreads) {
       const uint32_t rc = sm.cand[p];
       int32_t i, j, k;
@@ -527,6 +531,11 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
         if (!(sm.owner[x] & kSet)) {
           atomicAdd(&sm.owner[x], 1u);
           any = true;
+          if (p == tid) {
+            if (n_crossed < 4u) crossed |= (unsigned long long)x << (16u * n_crossed);
+            else if (n_crossed < 8u) crossed_hi |= (unsigned long long)x << (16u * (n_crossed - 4u));
+            ++n_crossed;
+          }
         }
       });
       if (any) {
@@ -534,35 +543,47 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
         sm.any_edge = 1;
       }
     }
-    if (tid == 0) sm.undecided = n_cand;
     __syncthreads();
     if (sm.any_edge) {
       // ---- B1: sweeps until every candidate is decided
       st.resolve_waves += 1;
       for (;;) {
         st.rounds += 1;
-        uint32_t done = 0;
+        bool waiting = false;  // one of this thread's candidates is still undecided after the sweep
         for (uint32_t p = tid; p < n_cand; p += kVisThreads) {
           const uint32_t pbit = 1u << (p & 31u);
           if (sm.decided[p >> 5] & pbit) continue;
           const uint32_t rc = sm.cand[p];
           const bool succ = (sm.has_succ[p >> 5] & pbit) != 0;
+          const bool remembered = p == tid && n_crossed <= 8u;
           if ((*(volatile uint32_t*)&sm.killed[rc >> 5] >> (rc & 31u)) & 1u) {
             atomicOr(&sm.decided[p >> 5], pbit);
-            ++done;
-            if (succ) prefix_walk(f, w, sm, rc, [&](uint32_t x) { if (!(sm.owner[x] & kSet)) atomicSub(&sm.owner[x], 1u); });
+            if (succ) {  // it does not cast: the cells it would have crossed stop waiting for it
+              if (remembered) {
+                for (uint32_t q = 0; q < n_crossed; ++q)
+                  atomicSub(&sm.owner[(uint32_t)((q < 4u ? crossed : crossed_hi) >> (16u * (q & 3u))) & 0xFFFFu], 1u);
+              } else {
+                prefix_walk(f, w, sm, rc, [&](uint32_t x) { if (!(sm.owner[x] & kSet)) atomicSub(&sm.owner[x], 1u); });
+              }
+            }
           } else if (*(volatile uint32_t*)&sm.owner[rc] == 0u) {
             atomicOr(&sm.decided[p >> 5], pbit);
             atomicOr(&sm.castbit[p >> 5], pbit);
-            ++done;
-            if (succ) prefix_walk(f, w, sm, rc, [&](uint32_t x) { if (!(sm.owner[x] & kSet)) atomicOr(&sm.killed[x >> 5], 1u << (x & 31u)); });
+            if (succ) {  // it casts: the cells it crosses do not
+              if (remembered) {
+                for (uint32_t q = 0; q < n_crossed; ++q) {
+                  const uint32_t x = (uint32_t)((q < 4u ? crossed : crossed_hi) >> (16u * (q & 3u))) & 0xFFFFu;
+                  atomicOr(&sm.killed[x >> 5], 1u << (x & 31u));
+                }
+              } else {
+                prefix_walk(f, w, sm, rc, [&](uint32_t x) { if (!(sm.owner[x] & kSet)) atomicOr(&sm.killed[x >> 5], 1u << (x & 31u)); });
+              }
+            }
+          } else {
+            waiting = true;
           }
         }
-        if (done) atomicSub(&sm.undecided, done);
-        __syncthreads();
-        const uint32_t left = sm.undecided;
-        __syncthreads();
-        if (left == 0) break;
+        if (!__syncthreads_or(waiting ? 1 : 0)) break;  // (one barrier per sweep: it also carries the verdict)
       }
       // cnt[] back to "unset"; casters compacted in visit order (read everything, then write)
       const uint32_t cper = (n_cand + kVisThreads - 1) / kVisThreads;
