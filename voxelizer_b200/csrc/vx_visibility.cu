@@ -297,10 +297,15 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
   const int32_t normal = w.face == 0 ? 0 : 1;
   const uint32_t enc_epoch = f.epoch << kEpochShift;
   const int32_t stride_j = f.g.nz, stride_i = f.g.ny * f.g.nz;
-  const uint32_t nx1 = (uint32_t)f.g.nx - 1u, ny1 = (uint32_t)f.g.ny - 1u, nz1 = (uint32_t)f.g.nz - 1u;
-  const uint32_t pend = f.pend;
+  // Leaving the grid (VoxelGrid.cpp:286-287,307) as ONE test on the packed position: OUT holds, per axis, the coordinate
+  // a step must not reach -- the size for a positive Step, 0 for a negative one (sic: Out = 0, the ray ends ON layer 0), or
+  // the wrapped -1 when the ray starts on layer 0 (it can only step out).  No coordinate of a ray that is still inside
+  // equals its OUT value, so "some field of P ^ OUT is zero" is exactly "the step left the grid".
+  constexpr uint32_t kFieldLow = 1u | (1u << kPosJ) | (1u << kPosK), kFieldHigh = (1u << (kPosJ - 1)) | (1u << (kPosK - 1)) | (1u << 31);
+  uint32_t pend = f.pend;
+  asm volatile("" : "+r"(pend));  // opaque: otherwise the compiler rebuilds it from ex / ey / ez in every iteration of the loop
   bool active = false, exhausted = false, in_face = false, refill = true;
-  uint32_t rc = 0, id = 0, len = 0, L = 0, P = 0;
+  uint32_t rc = 0, id = 0, len = 0, L = 0, P = 0, OUT = 0;
   int32_t dPx = 0, dPy = 0, dPz = 0, dLx = 0, dLy = 0, dLz = 0;
   float tx = 0.f, ty = 0.f, tz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
   for (;;) {
@@ -330,6 +335,8 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
             dLy = r0.sy * stride_j;
             dLz = r0.sz;
             P = (uint32_t)i | ((uint32_t)j << kPosJ) | ((uint32_t)k << kPosK);
+            OUT = (r0.sx > 0 ? (uint32_t)f.g.nx : (i == 0 ? kPosMaskIJ : 0u)) | ((r0.sy > 0 ? (uint32_t)f.g.ny : (j == 0 ? kPosMaskIJ : 0u)) << kPosJ) |
+                  ((r0.sz > 0 ? (uint32_t)f.g.nz : (k == 0 ? 0x3FFu : 0u)) << kPosK);
             L = lin(f.g, i, j, k);
             active = true;
             in_face = true;
@@ -365,11 +372,10 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
       tz = a01 ? tz : ntz;
       P += (uint32_t)(a0 ? dPx : (a1 ? dPy : dPz));
       L += (uint32_t)(a0 ? dLx : (a1 ? dLy : dLz));
-      const uint32_t pos = a0 ? (P & kPosMaskIJ) : (a1 ? ((P >> kPosJ) & kPosMaskIJ) : (P >> kPosK));
-      const uint32_t lim = a0 ? nx1 : (a1 ? ny1 : nz1);
       // leaves the grid (pos == Out after a positive step; 0 or wrapped after a negative one: Out = 0 there, and
       // a step to -1 ends at the top of the reference loop), or reaches the end voxel: the ray misses
-      finished = (pos - 1u >= lim) | (P == pend);
+      const uint32_t diff = P ^ OUT;
+      finished = (((diff - kFieldLow) & ~diff & kFieldHigh) != 0u) | (P == pend);
       vx_red_max(&f.memo[Lc], enc_epoch | id);
       ++len;
       bool hit = false;
