@@ -64,6 +64,27 @@ def test_reader_and_targets(port, tmp_path):
         assert written == targets.tolist()
 
 
+def test_direct_loader_matches_reference_shaped_loader(tmp_path):
+    """KittiReader::loadInto (what the pipeline's reader threads call) against KittiReader::load."""
+    import os
+    seq = make_sequence(str(tmp_path / "seq"), 4, 8, 64)
+    for t in range(4):
+        a = vx.read_scan(seq, t, direct=False)
+        b = vx.read_scan(seq, t, direct=True)
+        xyzr, raw = np.fromfile(os.path.join(seq, "velodyne", f"{t:06d}.bin"), np.float32).reshape(-1, 4), \
+            np.fromfile(os.path.join(seq, "labels", f"{t:06d}.label"), np.uint32)
+        assert np.array_equal(a[0].view(np.uint32), xyzr.view(np.uint32)) and np.array_equal(b[0].view(np.uint32), xyzr.view(np.uint32))
+        assert np.array_equal(a[1], raw & 0xFFFF) and np.array_equal(b[1], raw)   # the device applies the mask to raw labels
+        assert a[2] == b[2] == int(((raw & 0xFFFF) > 0).sum())
+        assert (raw >> 16).any()                                                   # the generator does write instance ids
+    assert vx.read_scan(seq, 0, direct=True, capacity=10) is None                 # does not fit: the pipeline falls back
+    with open(os.path.join(seq, "labels", "000002.label"), "ab") as f:           # one label too many
+        f.write(b"\0\0\0\0")
+    for direct in (False, True):
+        with pytest.raises(vx.VxError, match="Inconsistent number of labels"):
+            vx.read_scan(seq, 2, direct=direct)
+
+
 def test_windows_match_reader_semantics():
     # last scan: the past window is {N-1} (the last scan is inserted twice), SURVEY.md A.5
     assert vx.window(10, 0, 70, 9) == (9, 10, 9, 10)

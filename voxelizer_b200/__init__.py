@@ -175,6 +175,7 @@ def host_lib():
         L.vxh_reader_num_poses.argtypes = [C.c_void_p]
         L.vxh_reader_poses.argtypes = [C.c_void_p, C.c_void_p]
         L.vxh_reader_window.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.vxh_reader_load.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.vxh_plan_targets.restype = C.c_uint32
         L.vxh_plan_targets.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.vxh_gen_data.restype = C.c_int
@@ -292,6 +293,28 @@ def read_poses(seq_dir: str):
         if n:
             H.vxh_reader_poses(h, _p(out))
         return H.vxh_reader_count(h), out
+    finally:
+        H.vxh_reader_free(h)
+
+
+def read_scan(seq_dir: str, t: int, direct: bool, capacity: int = 1 << 20):
+    """Scan t through the host KittiReader: direct=True is the pipeline's loader (raw labels into caller memory),
+    False the reference-shaped one (labels & 0xFFFF).  Returns (xyzr [n,4], labels [n], labelled) or None if the scan
+    does not fit `capacity` points."""
+    H = host_lib()
+    h = H.vxh_reader_open(seq_dir.encode())
+    if not h:
+        raise VxError(H.vxh_last_error().decode())
+    try:
+        xyzr = np.zeros((capacity, 4), np.float32)
+        labels = np.zeros(capacity, np.uint32)
+        n, labelled = C.c_uint32(0), C.c_uint32(0)
+        rc = H.vxh_reader_load(h, t, int(direct), _p(xyzr), _p(labels), capacity, C.byref(n), C.byref(labelled))
+        if rc < 0:
+            raise VxError(H.vxh_last_error().decode())
+        if rc == 1:
+            return None
+        return xyzr[: n.value].copy(), labels[: n.value].copy(), int(labelled.value)
     finally:
         H.vxh_reader_free(h)
 

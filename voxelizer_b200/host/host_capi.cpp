@@ -124,6 +124,30 @@ void vxh_reader_window(void* r, int32_t prior, int32_t past, int32_t idx, int32_
   k->window(idx, out4[0], out4[1], out4[2], out4[3]);
 }
 
+// One scan through either loader: direct = KittiReader::loadInto (raw labels, straight into caller memory), else
+// KittiReader::load (labels masked with 0xFFFF).  Returns 0, 1 = does not fit `capacity`, -1 = error (vxh_last_error).
+int vxh_reader_load(void* r, uint32_t t, int direct, float* xyzr, uint32_t* labels, uint32_t capacity, uint32_t* points, uint32_t* labelled) {
+  try {
+    const vxb::KittiReader* k = static_cast<vxb::KittiReader*>(r);
+    if (direct) return k->loadInto(t, xyzr, labels, capacity, *points, *labelled) ? 0 : 1;
+    vxb::Laserscan scan;
+    std::vector<uint32_t> lab;
+    k->load(t, scan, lab);
+    if (scan.size() > capacity) return 1;
+    *points = scan.size();
+    *labelled = 0;
+    for (const uint32_t l : lab) *labelled += l > 0 ? 1u : 0u;
+    if (*points) {
+      std::memcpy(xyzr, scan.xyzr.data(), size_t(*points) * 16);
+      std::memcpy(labels, lab.data(), size_t(*points) * 4);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
 // target list (gen_data.cpp:62,129-141).  Returns the number of targets; writes at most cap.
 uint32_t vxh_plan_targets(void* cfg, uint32_t scan_count, const float* poses16, uint32_t n_poses, uint32_t* out, uint32_t cap) {
   std::vector<vxb::Matrix4f> poses(n_poses);
