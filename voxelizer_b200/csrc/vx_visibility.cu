@@ -20,9 +20,11 @@
 //          crossed are CANDIDATES.
 //       B  which candidates cast?  c casts iff no CASTING candidate visited earlier crosses c with
 //          the in-face part of its ray (rays are monotone per axis: they never re-enter the face).
-//          Counters: cnt[c] = undecided earlier candidates crossing c (their crossed cells are remembered in registers).  killed -> no cast (releases
+//          Counters: cnt[c] = undecided earlier candidates crossing c.  killed -> no cast (releases
 //          its successors); cnt == 0 -> casts (kills its successors).  Monotone, so any thread
-//          interleaving gives the reference's answer; chains resolve in as many sweeps as they are long.
+//          interleaving gives the reference's answer; chains resolve in as many sweeps as they are long
+//          (one barrier per sweep; a thread remembers in registers which candidates its candidate's ray
+//          crosses, so a sweep does not walk the ray again).
 //       C  casters get ray ids in visit order and trace: RED.MAX(memo[cell], id) = "latest ray wins";
 //          hit[id] is one bit set when the ray ends on an occupied cell.  Rays are pulled from a
 //          queue by the lanes of few warps and refilled as they end, so that a long ray does not
@@ -32,8 +34,8 @@
 //   * only booleans are observable (isOccluded / isInvalid, VoxelGrid.cpp:65-73).
 //
 // Latency- and issue-bound, not HBM-bound.  The occupancy test of a ray step reads a shared-memory
-// bitmap of 4x4x1-voxel blocks (5 % of the steps need the exact bit from global memory; that load is
-// issued one loop iteration before it is consumed).  Global traffic: one memo read per live visit,
+// bitmap of 4x4x1-voxel blocks (5 % of the steps need the exact bit from global memory); leaving the
+// grid is one zero-field test on the packed position (trace_warp).  Global traffic: one memo read per live visit,
 // one fire-and-forget RED per ray step, one hit-bit gather per live visit.
 #include "vx_launch.h"
 
