@@ -63,3 +63,45 @@ def test_division_free_floor_matches_ieee_division(res):
         assert not fast[~np.isfinite(v)].any()                          # NaN / infinity always take the IEEE path
         fast_share.append(fast.mean())
     assert fast_share[0] > 0.999                                         # the fallback is rare for ordinary points
+
+
+def test_packed_out_of_grid_test_equals_the_per_axis_rule():
+    """trace_warp (vx_visibility.cu) decides "the step left the grid" with ONE test on the packed position
+    P = i | j << 11 | k << 22: some field of P ^ OUT is zero, where OUT holds per axis the size (positive Step), 0
+    (negative Step: Out = 0, the ray ends ON layer 0) or the wrapped -1 (negative Step from layer 0).  Mirror of that
+    arithmetic against the reference's rule (VoxelGrid.cpp:286-287,307: pos == Out after the step, or pos < 0 at the
+    top of the next iteration), on random walks through small and maximal grids."""
+    rng = np.random.default_rng(11)
+    M32 = 0xFFFFFFFF
+    LOW = 1 | (1 << 11) | (1 << 22)
+    HIGH = (1 << 10) | (1 << 21) | (1 << 31)
+
+    def has_zero_field(x):
+        return (((x - LOW) & M32) & (~x & M32) & HIGH) != 0
+
+    checked = 0
+    for trial in range(4000):
+        n = [int(rng.choice([1, 2, 3, 7, 32, 256, 2047])), int(rng.choice([1, 2, 5, 64, 256, 2047])), int(rng.choice([1, 2, 10, 32, 64, 1023]))]
+        pos = [int(rng.integers(0, n[a])) for a in range(3)]
+        if rng.random() < 0.4:  # start on a boundary layer
+            a = int(rng.integers(0, 3))
+            pos[a] = 0 if rng.random() < 0.5 else n[a] - 1
+        step = [int(rng.choice([-1, 1])) for _ in range(3)]
+        out_ref = [n[a] if step[a] > 0 else 0 for a in range(3)]                      # VoxelGrid.cpp:258-259,265-266
+        full = [0x7FF, 0x7FF, 0x3FF]
+        out_field = [n[a] if step[a] > 0 else (full[a] if pos[a] == 0 else 0) for a in range(3)]
+        OUT = out_field[0] | (out_field[1] << 11) | (out_field[2] << 22)
+        P = pos[0] | (pos[1] << 11) | (pos[2] << 22)
+        assert not has_zero_field(P ^ OUT)                                           # a ray that is inside is never "out"
+        shift = [0, 11, 22]
+        for _ in range(6000):
+            a = int(rng.integers(0, 3))
+            pos[a] += step[a]
+            P = (P + (step[a] << shift[a])) & M32
+            ref_out = pos[a] == out_ref[a] or pos[a] < 0
+            assert has_zero_field(P ^ OUT) == ref_out, (n, pos, step, a)
+            checked += 1
+            if ref_out:
+                break
+            assert P == pos[0] | (pos[1] << 11) | (pos[2] << 22)                     # no field disturbed another one
+    assert checked > 50000
