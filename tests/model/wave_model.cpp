@@ -24,6 +24,13 @@
 //      hit[id] = the ray ended on an occupied cell.
 //   D. apply the visit rule: occlusion pass  occluded[c] = hit[owner] (last visit wins); invalid
 //      pass  hit[owner] == 0 kills the cell.
+//
+// mode 1 (not in the product kernel yet: experiments/r01_rays_in_flight.patch) additionally keeps the rays of an
+// INVALID pass in flight across waves: a ray is cast, walked until it has left its wave's face and parked; before
+// a wave's snapshot every parked ray is advanced until it is strictly beyond the wave's plane in its direction of
+// travel (plus a random number of steps); the visits are logged and applied when every ray has ended.  "The plane
+// lies beyond the ray's end voxel" also counts as safe, guarded by an overshoot detector that re-runs the pass
+// without that rule.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -45,6 +52,16 @@ struct Model {
   uint32_t max_live = 2048;
   uint32_t max_cols = 512;
   uint64_t rng = 1;
+  // rays in flight (mode 1, invalid passes)
+  int mode = 0;
+  bool in_flight = false, conservative = false, overshoot = false;
+  struct Parked {
+    VxRay r;
+    uint32_t id;
+  };
+  std::vector<Parked> pool;
+  std::vector<std::pair<size_t, uint32_t>> visit_log;  // (cell, owner) of every live visit of the pass
+  uint64_t n_parked = 0, n_redo = 0;
   // stats
   uint64_t n_rays = 0, n_steps = 0, n_waves = 0, n_resolve_waves = 0, n_rounds = 0, max_rounds = 0, n_prefix_steps = 0, n_unset = 0;
 
@@ -89,6 +106,47 @@ struct Model {
     return d[normal] > 1.0001f * other;
   }
 
+  // one iteration of the trace loop for a ray that is parked on a cell it has not examined yet; true = the ray ended
+  bool step_parked(Parked& p) {
+    VxRay& r = p.r;
+    const size_t L = lin(r.i, r.j, r.k);
+    if (bit(occ, L)) {
+      hit[p.id] = 1;
+      return true;
+    }
+    memo[L] = std::max(memo[L], (epoch << 25) | p.id);
+    ++n_steps;
+    if (!r.advance()) return true;
+    if (!r.inside(g)) return true;
+    if (!conservative) {  // past the end voxel's coordinate?  then "ends before the plane" was not a safe assumption
+      if ((r.sx > 0 && r.i > r.ex) || (r.sx < 0 && r.i < r.ex) || (r.sy > 0 && r.j > r.ey) || (r.sy < 0 && r.j < r.ey) ||
+          (r.sz > 0 && r.k > r.ez) || (r.sz < 0 && r.k < r.ez))
+        overshoot = true;
+    }
+    return false;
+  }
+  bool safe_for(const Parked& p, int plane_axis, int32_t c) const {
+    const int32_t pa = plane_axis == 0 ? p.r.i : p.r.j, s = plane_axis == 0 ? p.r.sx : p.r.sy, end = plane_axis == 0 ? p.r.ex : p.r.ey;
+    const bool beyond = s > 0 ? pa > c : pa < c;
+    const bool ends_before = !conservative && (s > 0 ? c > end : c < end);
+    return beyond || ends_before;
+  }
+  // before the snapshot of a wave on (plane_axis, c); drain: until every ray has ended
+  void advance_pool(int plane_axis, int32_t c, bool drain) {
+    shuffle(pool);
+    std::vector<Parked> keep;
+    for (Parked& p : pool) {
+      bool ended = false;
+      uint32_t extra = drain ? 0 : next_rand() % 4;  // the kernel advances a minimum number of steps per wave
+      while (!ended && (drain || !safe_for(p, plane_axis, c) || extra > 0)) {
+        if (extra) --extra;
+        ended = step_parked(p);
+      }
+      if (!ended) keep.push_back(p);
+    }
+    pool.swap(keep);
+  }
+
   void run_wave(const Wave& w, const float* e, bool inv, uint32_t& id_base) {
     const int normal = w.face == 0 ? 0 : 1;
     // ---- A: live cells in visit order, rank lookup, snapshot
@@ -104,6 +162,7 @@ struct Model {
       }
     const uint32_t n = uint32_t(cells.size());
     ++n_waves;
+    if (in_flight) advance_pool(w.face == 0 ? 0 : 1, w.fixed, false);
     const uint32_t SET = 0x80000000u;
     std::vector<uint32_t> owner(n, 0);  // 0 = candidate; SET | id otherwise.  Doubles as cnt[] during B.
     std::vector<uint32_t> cand;
@@ -189,8 +248,14 @@ struct Model {
       ++n_rays;
       VxRay r;
       r.begin(g, cells[rc].i, cells[rc].j, cells[rc].k, e[0], e[1], e[2]);
-      bool h = false, in_face = true;
+      bool h = false, in_face = true, parked = false;
       for (;;) {
+        if (in_flight && !in_face && next_rand() % 3 != 0) {  // park it (sometimes a few steps later)
+          pool.push_back(Parked{r, id});
+          ++n_parked;
+          parked = true;
+          break;
+        }
         if (!r.inside(g)) break;
         const size_t L = lin(r.i, r.j, r.k);
         if (bit(occ, L)) {
@@ -206,7 +271,7 @@ struct Model {
         if (r.next_axis() == normal) in_face = false;
         if (!r.advance()) break;
       }
-      hit[id] = h ? 1 : 0;
+      if (!parked) hit[id] = h ? 1 : 0;
     }
     id_base += uint32_t(casters.size());
     // ---- D
@@ -214,6 +279,10 @@ struct Model {
       const size_t L = lin(cells[r].i, cells[r].j, cells[r].k);
       if (!(owner[r] & SET)) {
         ++n_unset;
+        continue;
+      }
+      if (in_flight) {  // the owner may still be in flight: the pass applies its log at its end
+        visit_log.emplace_back(L, owner[r] & 0x1FFFFFFu);
         continue;
       }
       const bool h = hit[owner[r] & 0x1FFFFFFu] != 0;
@@ -247,19 +316,43 @@ struct Model {
     }
   }
 
-  void run_pass(const float* e, bool inv) {
+  void bump_epoch() {
     epoch += 1;
     if (epoch >= 127) {
       std::fill(memo.begin(), memo.end(), 0u);
       epoch = 1;
     }
-    std::fill(hit.begin(), hit.end(), 0);
-    uint32_t id_base = 0;
-    const int32_t shells = vx_num_shells(g.nx, g.ny);
-    for (int32_t o = 0; o < shells; ++o) {
-      run_face(0, g.nx - 1 - o, g.ny, e, inv, id_base);
-      run_face(1, o, g.nx - o - 1, e, inv, id_base);
-      run_face(2, g.ny - 1 - o, g.nx - o - 1, e, inv, id_base);
+  }
+
+  void run_pass(const float* e, bool inv) {
+    in_flight = mode == 1 && inv;
+    conservative = false;
+    const uint64_t rays0 = n_rays, steps0 = n_steps;
+    for (;;) {
+      bump_epoch();  // (a new epoch also forgets the marks of an abandoned attempt)
+      std::fill(hit.begin(), hit.end(), 0);
+      pool.clear();
+      visit_log.clear();
+      overshoot = false;
+      uint32_t id_base = 0;
+      const int32_t shells = vx_num_shells(g.nx, g.ny);
+      for (int32_t o = 0; o < shells; ++o) {
+        run_face(0, g.nx - 1 - o, g.ny, e, inv, id_base);
+        run_face(1, o, g.nx - o - 1, e, inv, id_base);
+        run_face(2, g.ny - 1 - o, g.nx - o - 1, e, inv, id_base);
+      }
+      if (!in_flight) return;
+      advance_pool(0, 0, true);
+      if (overshoot && !conservative) {  // nothing of the pass has been applied yet: run it again, conservatively
+        conservative = true;
+        n_rays = rays0;
+        n_steps = steps0;
+        ++n_redo;
+        continue;
+      }
+      for (const auto& v : visit_log)
+        if (!hit[v.second]) setbit(live, v.first, false);
+      return;
     }
   }
 };
@@ -273,9 +366,21 @@ extern "C" {
 // Outputs (bytes 0/1, output order): occluded = occlusions_ > -1, invalid = reference isInvalid after
 // all passes.  stats8: rays, steps, waves, waves needing resolution, total rounds, max rounds, prefix
 // steps, live cells left without an owner (must be 0).
+void wm_run_mode(int mode, const int32_t* size3, float res, const float* off3, const uint8_t* occ_bytes, uint32_t n_endpoints,
+                 const float* endpoints, uint32_t max_live, uint64_t seed, uint8_t* occluded, uint8_t* invalid, uint64_t* stats8,
+                 uint64_t* extra2);
+
 void wm_run(const int32_t* size3, float res, const float* off3, const uint8_t* occ_bytes, uint32_t n_endpoints,
             const float* endpoints, uint32_t max_live, uint64_t seed, uint8_t* occluded, uint8_t* invalid, uint64_t* stats8) {
+  wm_run_mode(0, size3, res, off3, occ_bytes, n_endpoints, endpoints, max_live, seed, occluded, invalid, stats8, nullptr);
+}
+
+// mode 1: rays of the invalid passes in flight across waves.  extra2: rays parked, passes run again conservatively.
+void wm_run_mode(int mode, const int32_t* size3, float res, const float* off3, const uint8_t* occ_bytes, uint32_t n_endpoints,
+                 const float* endpoints, uint32_t max_live, uint64_t seed, uint8_t* occluded, uint8_t* invalid, uint64_t* stats8,
+                 uint64_t* extra2) {
   Model m;
+  m.mode = mode;
   m.g.nx = size3[0];
   m.g.ny = size3[1];
   m.g.nz = size3[2];
@@ -314,6 +419,10 @@ void wm_run(const int32_t* size3, float res, const float* off3, const uint8_t* o
     stats8[5] = m.max_rounds;
     stats8[6] = m.n_prefix_steps;
     stats8[7] = m.n_unset;
+  }
+  if (extra2) {
+    extra2[0] = m.n_parked;
+    extra2[1] = m.n_redo;
   }
 }
 
