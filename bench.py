@@ -6,17 +6,27 @@
 
 A STEP is one pass of the hot path over one whole synthetic sequence: 4541 HDL-64-like scans
 (SemanticKITTI seq-00 shape), configs/semantic_kitti.cfg => 909 target frames, each aggregating its
-window of up to 71 scans (BASELINE.json configs[1]).  With N GPUs every rank runs its own sequence
-(seed 1234 + rank): frames shard naturally, there is no data-path collective (weak scaling); the only
-communication is the barrier and the max-reduction of the per-rank device times.
+window of up to 71 scans (BASELINE.json configs[1]).
 
-value : frames/s with all scans already resident in HBM and outputs left in HBM.
-e2e   : frames/s through the C ABI with HOST buffers: every step uploads every scan from pinned host
-        memory and copies every output file image back to pinned host memory.
+value  : frames/s with all scans already resident in HBM and outputs left in HBM (CUDA events).
+e2e    : frames/s through the C ABI with HOST buffers: every step uploads every scan from pinned host memory
+         and copies every output file image back to pinned host memory; steps are submitted asynchronously
+         (vx_submit_frames / vx_wait), so the upload of step k+1 overlaps the traversal of step k.
+parity_check : the e2e outputs of the frames the cpu_baseline leg computed with the reference's own code
+         (oracle/_ref, same seed-1234 sequence) compared by sha256; a mismatch makes the run fail.
+extra_configs : (N = 1) BASELINE configs[2..4] -- dense stride-1 windows, the 512x512x64 @ 0.1 m stress grid,
+         1001-scan windows -- each with a reference sample beside it, outside the headline's timed region.
+strong : (N > 1) ONE seed-1234 sequence, semantic_kitti_dense.cfg, contiguous target ranges + window halo per rank,
+         scans uploaded from pinned host memory, outputs hashed and compared with a single-GPU run of the same job
+         on rank 0 (BASELINE configs[2]); the stress grid sharded the same way (configs[3]).
+With N GPUs the headline `value` stays the weak-scaling figure (every rank its own sequence, seed 1234 + rank; no
+data-path collective: the only communication is the barrier and the reductions of the per-rank times / digests).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -33,6 +43,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "voxelized frames/sec (256x256x32 @0.2m)"
 UNIT = "frames/s"
 CAP_POINTS = 128000  # 64 beams x 2000 azimuth steps
+CONFIGS = os.path.join(ROOT, "configs")
+
+
+def cfg_file(name: str) -> str:
+    return os.path.join(CONFIGS, name + ".cfg")
 
 
 def parse_args():
@@ -46,7 +61,11 @@ def parse_args():
     ap.add_argument("--frames-in-flight", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (N = 1) / strong (N > 1)")
+    ap.add_argument("--time-budget", type=float, default=330.0, help="seconds after which optional legs are skipped")
     ap.add_argument("--ref-cores", type=int, default=0)
+    ap.add_argument("--ref-frames", type=int, default=0, help="reference arm: frames per step (default: one per core)")
+    ap.add_argument("--ref-passes", type=int, default=-1, help="reference arm: time only this many updateInvalid passes per frame")
     return ap.parse_args()
 
 
@@ -61,37 +80,103 @@ def measured_peak_gbs():
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU code (oracle/_ref when it was compiled, else the port)
+# reference arm: the reference's own CPU code (oracle/_ref when it was compiled, else the port).  Nothing of the
+# product package is imported here: the synthetic generator is loaded through the small ctypes shim below, the
+# config comes from the oracle's own parser.
 # ------------------------------------------------------------------------------------------------------
+class _SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_beams", C.c_uint32), ("n_azimuth", C.c_uint32)] + [
+        (n, C.c_float) for n in ("elev_top_deg", "elev_bottom_deg", "max_return_m", "sensor_height_m", "speed_m", "noise_m",
+                                 "unlabeled_frac", "outlier_frac", "sway_amp_m", "yaw_amp_rad")]
+
+
+class _Synth:
+    """voxelizer_b200/lib/libvxsynth.so (a plain CPU generator; it links nothing of the CUDA library)."""
+
+    def __init__(self):
+        L = C.CDLL(os.path.join(ROOT, "voxelizer_b200", "lib", "libvxsynth.so"))
+        L.vxs_default_params.argtypes = [C.POINTER(_SynthParams)]
+        L.vxs_velo_pose.argtypes = [C.POINTER(_SynthParams), C.c_uint32, C.c_void_p]
+        L.vxs_generate_many.restype = C.c_int
+        L.vxs_generate_many.argtypes = [C.POINTER(_SynthParams), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        self.L = L
+
+    def params(self, seed):
+        p = _SynthParams()
+        self.L.vxs_default_params(C.byref(p))
+        p.seed = seed
+        return p
+
+    def generate(self, p, t0, n, threads):
+        xyzr = np.empty((n, CAP_POINTS, 4), np.float32)
+        lab = np.empty((n, CAP_POINTS), np.uint32)
+        counts = np.zeros(n, np.uint32)
+        if self.L.vxs_generate_many(C.byref(p), t0, n, xyzr.ctypes.data, lab.ctypes.data, CAP_POINTS, counts.ctypes.data, threads) != 0:
+            raise RuntimeError("vxs_generate_many failed")
+        return xyzr, lab, counts
+
+    def poses(self, p, n):
+        out = np.empty((n, 16), np.float64)
+        tmp = np.empty(16, np.float64)
+        for t in range(n):
+            self.L.vxs_velo_pose(C.byref(p), t, tmp.ctypes.data)
+            out[t] = tmp.reshape(4, 4).T.reshape(16)
+        return out.astype(np.float32)
+
+
 _REF_DATA = {}  # inherited by the forked workers (no pickling of the scans)
+_W = {}         # per worker: oracle, config and the two grids, created ONCE (gen_data.cpp:55-56) and clear()ed per frame
 
 
-def _ref_worker(target):
-    kind, cfg_file, scans, labels, poses, n_past = (_REF_DATA[k] for k in ("kind", "cfg", "scans", "labels", "poses", "n_past"))
+def _ref_init(kind, cfg_path, all_ready):
     from oracle.oracle import Oracle
-    import tempfile
     orc = Oracle(kind)
-    cfg = orc.load_config(cfg_file)
+    cfg = orc.load_config(cfg_path)
     p = cfg.pod
+    _W.update(orc=orc, cfg=cfg, gi=orc.grid(p.voxelSize, list(p.minExtent), list(p.maxExtent)),
+              gt=orc.grid(p.voxelSize, list(p.minExtent), list(p.maxExtent)))
+    all_ready.wait()  # no worker takes a task before every worker has built its grids: nothing of this is ever timed
+
+
+def _ref_frame(job):
+    """One iteration of gen_data.cpp:89-121 for target `job[0]`; returns stage times and the sha256 of the four files."""
+    import tempfile
+    target, max_passes = job
+    orc, cfg, gi, gt = _W["orc"], _W["cfg"], _W["gi"], _W["gt"]
+    scans, labels, poses, n_past = (_REF_DATA[k] for k in ("scans", "labels", "poses", "n_past"))
     ids = list(range(target, min(len(scans), target + n_past + 1)))
-    t0 = time.perf_counter()
-    gi = orc.grid(p.voxelSize, list(p.minExtent), list(p.maxExtent))
-    gt = orc.grid(p.voxelSize, list(p.minExtent), list(p.maxExtent))
-    anchor = poses[target]
     pick = lambda idx: ([scans[i] for i in idx], [labels[i] for i in idx], np.stack([poses[i] for i in idx]))
     ps, pl, pp = pick(ids[:1])
     qs, ql, qp = pick(ids[1:])
+    anchor = poses[target]
+    t0 = time.perf_counter()
+    gi.clear()                                            # gen_data.cpp:89-90
+    gt.clear()
     gi.fill(cfg, anchor, ps, pl, pp)                      # gen_data.cpp:96-98
     gt.fill(cfg, anchor, ps, pl, pp)
     gt.fill(cfg, anchor, qs, ql, qp)
+    t1 = time.perf_counter()
     gi.update_occlusions()                                # gen_data.cpp:102-103
     gt.update_occlusions()
-    for i in ids[1:]:                                     # gen_data.cpp:113-116
+    t2 = time.perf_counter()
+    pass_s = []
+    todo = ids[1:] if max_passes < 0 else ids[1:1 + max_passes]
+    for i in todo:                                        # gen_data.cpp:113-116
+        tp = time.perf_counter()
         gt.update_invalid(orc.endpoint(anchor, poses[i]))
+        pass_s.append(time.perf_counter() - tp)
+    t3 = time.perf_counter()
+    hashes = {}
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
         gi.save(d, "%06d" % target, "input")              # gen_data.cpp:120-121
         gt.save(d, "%06d" % target, "target")
-    return time.perf_counter() - t0
+        t4 = time.perf_counter()
+        if max_passes < 0:                                # complete frames only: these are what the GPU arm is checked against
+            for ext in ("bin", "label", "occluded", "invalid"):
+                with open(os.path.join(d, "%06d.%s" % (target, ext)), "rb") as fh:
+                    hashes[ext] = hashlib.sha256(fh.read()).hexdigest()
+    return dict(target=target, total=t4 - t0, fill=t1 - t0, occl=t2 - t1, passes=pass_s, save=t4 - t3, hashes=hashes,
+                n_passes_full=len(ids) - 1)
 
 
 def run_reference(args):
@@ -100,51 +185,68 @@ def run_reference(args):
         return 0
     import multiprocessing as mp
 
-    import voxelizer_b200 as vx
-    from oracle.oracle import have_ref
-    from util import cfg_path
+    from oracle.oracle import Oracle, have_ref
 
     kind = "ref" if have_ref() else "port"
+    parent = Oracle(kind)  # dlopens oracle/_ref/libvx_ref.so (or the port) in THIS process, before the fork
+    cfg = parent.load_config(cfg_file(args.config))
     cores = args.ref_cores or (os.cpu_count() or 1)
-    cfg = vx.Config(cfg_path(args.config))
     stride = max(1, cfg.pod.stride_num)
     n_past = cfg.pod.pastScans
-    n_frames = cores
+    n_frames = args.ref_frames or cores
     n_scans = stride * (n_frames - 1) + n_past + 1
-    params = vx.synth_params(seed=1234)
-    xyzr = np.empty((n_scans, CAP_POINTS, 4), np.float32)
-    lab = np.empty((n_scans, CAP_POINTS), np.uint32)
-    counts = vx.synth_generate_many(params, 0, n_scans, xyzr.ctypes.data, lab.ctypes.data, CAP_POINTS)
+    synth = _Synth()
+    params = synth.params(1234)
+    xyzr, lab, counts = synth.generate(params, 0, n_scans, max(1, min(64, os.cpu_count() or 1)))
     scans = [xyzr[t, : counts[t]] for t in range(n_scans)]
     labels = [lab[t, : counts[t]] & 0xFFFF for t in range(n_scans)]
-    poses = vx.synth_velo_poses(params, n_scans).astype(np.float32)
-    _REF_DATA.update(kind=kind, cfg=cfg_path(args.config), scans=scans, labels=labels, poses=poses, n_past=n_past)
-    jobs = [stride * i for i in range(n_frames)]
-    step_s = []
+    poses = synth.poses(params, n_scans)
+    _REF_DATA.update(scans=scans, labels=labels, poses=poses, n_past=n_past)
+    jobs = [(stride * i, args.ref_passes) for i in range(n_frames)]
+    step_s, frames = [], []
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    workers = min(cores, n_frames)
+    with ctx.Pool(workers, initializer=_ref_init, initargs=(kind, cfg_file(args.config), ctx.Barrier(workers))) as pool:
+        single = pool.apply(_ref_frame, (jobs[0],))       # one frame with the machine to itself: the 1-thread figure
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            per_frame = pool.map(_ref_worker, jobs, chunksize=1)
+            frames = pool.map(_ref_frame, jobs, chunksize=1)
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 step_s.append(dt)
     ms = 1e3 * float(np.mean(step_s))
     value = n_frames / (ms / 1e3)
-    sample = (f"{n_frames} full-window frames ({n_past + 1} scans each, targets 0,{stride},..) of the same synthetic sequence per step, "
-              f"one frame per process on {cores} host processes; fill + updateOcclusions x2 + updateInvalid x{n_past} + saveVoxelGrid "
-              f"to tmpfs; mean single-frame time {np.mean(per_frame):.2f} s")
+    mean = lambda k: float(np.mean([f[k] for f in frames]))
+    n_timed = len(frames[0]["passes"])
+    pass_profile = [float(np.mean([f["passes"][p] for f in frames if len(f["passes"]) > p])) for p in range(n_timed)]
+    sample = (f"{n_frames} frames ({n_past + 1}-scan windows, targets 0,{stride},..) of the seed-1234 synthetic sequence per step, one frame "
+              f"per process on {workers} host processes (grids built once per process, clear() per frame); clear + fill + "
+              f"updateOcclusions x2 + updateInvalid x{n_timed if args.ref_passes >= 0 else n_past} + saveVoxelGrid to tmpfs; mean "
+              f"single-frame time under load {mean('total'):.2f} s, alone {single['total']:.2f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+u32", "data": "synthetic",
-        "config": {"workload": f"{args.config}.cfg, synthetic seq-00-shaped sequence, full {n_past + 1}-scan windows", "frames_per_step": n_frames},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if kind == "ref" else "port", "sample": sample},
+        "config": {"workload": f"{args.config}.cfg, synthetic seq-00-shaped sequence (seed 1234), full {n_past + 1}-scan windows", "frames_per_step": n_frames},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference" if kind == "ref" else "port", "sample": sample,
+                         "single_thread": {"value": 1.0 / single["total"], "unit": UNIT, "cores": 1, "seconds_per_frame": single["total"]}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "stage_s_per_frame": {"fill": mean("fill"), "occlusions": mean("occl"), "invalid_timed": float(np.mean([sum(f["passes"]) for f in frames])),
+                              "save": mean("save"), "passes_timed": n_timed, "passes_full": frames[0]["n_passes_full"],
+                              "alone": {k: single[k] for k in ("fill", "occl", "save", "total")}},
+        "pass_profile_s": pass_profile,
+        "frame_hashes": {str(f["target"]): f["hashes"] for f in frames if f["hashes"]},
     }
     print(json.dumps(line))
     return 0
+
+
+def reference_subprocess(config, extra, timeout=900):
+    """Runs the reference arm as a child process and returns its JSON line (dict)."""
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--config", config] + extra, capture_output=True, text=True, timeout=timeout)
+    return json.loads(out.stdout.strip().splitlines()[-1])
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -179,13 +281,118 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+class Sequence:
+    """Scans [t0, t0 + n) of a synthetic sequence in pinned host memory."""
+
+    def __init__(self, vx, seed, t0, n, threads):
+        self.vx, self.t0, self.n = vx, t0, n
+        self.params = vx.synth_params(seed=seed)
+        self.pin_xyzr = vx.PinnedBuffer(max(1, n) * CAP_POINTS * 16)
+        self.pin_lab = vx.PinnedBuffer(max(1, n) * CAP_POINTS * 4)
+        self.counts = vx.synth_generate_many(self.params, t0, n, self.pin_xyzr.ptr, self.pin_lab.ptr, CAP_POINTS, threads=threads)
+        lab = self.pin_lab.array.view(np.uint32).reshape(max(1, n), CAP_POINTS)
+        self.labelled = np.array([int(((lab[t, : self.counts[t]] & 0xFFFF) > 0).sum()) for t in range(n)], np.uint32)
+
+    def upload(self, be, first=None, last=None, id_offset=0):
+        """Scans [first, last) (absolute indices) under id = index + id_offset."""
+        first = self.t0 if first is None else first
+        last = self.t0 + self.n if last is None else last
+        for t in range(first, last):
+            k = t - self.t0
+            be.upload_scan_ptr(t + id_offset, self.pin_xyzr.ptr + k * CAP_POINTS * 16, self.pin_lab.ptr + k * CAP_POINTS * 4, int(self.counts[k]))
+
+    def free(self):
+        self.pin_xyzr.free()
+        self.pin_lab.free()
+
+
+def plan_frames(vx, cfg, n_scans_total, poses, seq, targets=None, id_offset=0):
+    """FrameSpecs exactly like gen_data: targets (stride walk), windows, the "labelled" gate, transforms.  `seq` must
+    hold every scan the chosen targets read.  Returns (specs, their targets, window points)."""
+    if targets is None:
+        targets = vx.plan_targets(cfg, n_scans_total, poses)
+    specs, kept, window_points = [], [], 0
+    c = lambda a, b: seq.counts[a - seq.t0:b - seq.t0]
+    lb = lambda a, b: seq.labelled[a - seq.t0:b - seq.t0]
+    for tgt in targets:
+        pb, pe, qb, qe = vx.window(n_scans_total, cfg.pod.priorScans, cfg.pod.pastScans, int(tgt))
+        pts = np.uint32(c(qb, qe).sum(dtype=np.uint32))
+        labc = np.uint32(lb(qb, qe).sum(dtype=np.uint32))
+        if not (np.float32(100.0) * np.float32(labc) / np.float32(pts) > 0):
+            continue  # "skipped."
+        anchor = poses[pe - 1]
+        ap_p, _ = vx.frame_transforms(anchor, poses[pb:pe])
+        ap_q, ep = vx.frame_transforms(anchor, poses[qb:qe])
+        specs.append(vx.FrameSpec(np.arange(pb, pe, dtype=np.uint32) + id_offset, ap_p, np.arange(qb, qe, dtype=np.uint32) + id_offset, ap_q, ep))
+        kept.append(int(tgt))
+        window_points += int(c(pb, pe).sum()) + int(c(qb, qe).sum())
+    return specs, kept, window_points
+
+
+def output_views(ring, be, n):
+    per = be.label_bytes + 3 * be.packed_bytes
+    outs = []
+    for k in range(n):
+        base = ring.array[k * per:(k + 1) * per]
+        outs.append(dict(label=base[: be.label_bytes], bin=base[be.label_bytes: be.label_bytes + be.packed_bytes],
+                         occluded=base[be.label_bytes + be.packed_bytes: be.label_bytes + 2 * be.packed_bytes],
+                         invalid=base[be.label_bytes + 2 * be.packed_bytes:]))
+    return outs
+
+
+def frame_digest(o):
+    return {k: hashlib.sha256(o[k]).hexdigest() for k in ("bin", "label", "occluded", "invalid")}
+
+
+def frame_digest_bytes(o):
+    h = hashlib.sha256()
+    for k in ("bin", "label", "occluded", "invalid"):
+        h.update(o[k])
+    return h.digest()
+
+
+def run_host_job(vx, be, seq, specs, ring, chunk):
+    """Frames through the C ABI with HOST buffers, in chunks of `chunk` frames (the ring holds one chunk): returns
+    (seconds spent between submit and wait, one 32-byte digest per frame).  Scans must be resident."""
+    digests, busy = [], 0.0
+    for a in range(0, len(specs), chunk):
+        part = specs[a:a + chunk]
+        outs = output_views(ring, be, len(part))
+        descs, keep = be.build_descs(part, outs)
+        t0 = time.perf_counter()
+        be.wait(be.submit_descs(descs, len(part)))
+        busy += time.perf_counter() - t0
+        digests += [frame_digest_bytes(o) for o in outs]
+    return busy, digests
+
+
+def reference_estimate(ref, n_passes):
+    """Seconds per frame of the reference from a sample that timed only its first updateInvalid passes: the remaining
+    passes are extrapolated with `ref['profile']` (per-pass seconds of complete configs[1] frames: the live set, and
+    with it the cost of a pass, shrinks from pass to pass) -- labelled as an extrapolation wherever it is printed."""
+    st = ref["stage_s_per_frame"]
+    timed = ref["pass_profile_s"]
+    k = len(timed)
+    if k >= n_passes:
+        inv = sum(timed[:n_passes])
+    else:
+        prof = ref.get("profile") or []
+        if prof and k and sum(prof[:k]) > 0:
+            scale = sum(timed) / sum(prof[:k])
+            tail = [prof[min(p, len(prof) - 1)] for p in range(k, n_passes)]
+            inv = sum(timed) + scale * sum(tail)
+        else:
+            inv = sum(timed) / max(1, k) * n_passes
+    return st["fill"] + st["occlusions"] + inv + st["save"]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import voxelizer_b200 as vx
-    from util import cfg_path
 
+    t_start = time.perf_counter()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,58 +414,42 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
 
     # ---- CPU baseline (rank 0, N=1 only): the reference arm as a subprocess, one step
-    cpu_baseline = None
+    cpu_baseline, ref_line = None, None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                                  "--config", args.config], capture_output=True, text=True, timeout=900)
-            cpu_baseline = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            ref_line = reference_subprocess(args.config, [])
+            cpu_baseline = ref_line["cpu_baseline"]
         except Exception as e:  # the baseline is reported, never required for the GPU number
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
     # ---- synthetic sequence of this rank, straight into pinned host memory
-    cfg = vx.Config(cfg_path(args.config))
+    cfg = vx.Config(cfg_file(args.config))
     n_scans = args.scans
-    params = vx.synth_params(seed=1234 + rank)
     t_gen = time.perf_counter()
-    pin_xyzr = vx.PinnedBuffer(n_scans * CAP_POINTS * 16)
-    pin_lab = vx.PinnedBuffer(n_scans * CAP_POINTS * 4)
-    counts = vx.synth_generate_many(params, 0, n_scans, pin_xyzr.ptr, pin_lab.ptr, CAP_POINTS, threads=max(1, (os.cpu_count() or 1) // max(1, world)))
-    poses = vx.synth_velo_poses(params, n_scans).astype(np.float32)
-    lab_view = pin_lab.array.view(np.uint32).reshape(n_scans, CAP_POINTS)
-    labelled = np.array([int(((lab_view[t, : counts[t]] & 0xFFFF) > 0).sum()) for t in range(n_scans)], np.uint32)
+    seq = Sequence(vx, 1234 + rank, 0, n_scans, host_threads)
+    poses = vx.synth_velo_poses(seq.params, n_scans).astype(np.float32)
     t_gen = time.perf_counter() - t_gen
 
     be = vx.Backend.from_config(cfg, device=local_rank, frames_in_flight=args.frames_in_flight,
                                 stream=torch.cuda.current_stream().cuda_stream)
-
-    def upload_all():
-        for t in range(n_scans):
-            be.upload_scan_ptr(t, pin_xyzr.ptr + t * CAP_POINTS * 16, pin_lab.ptr + t * CAP_POINTS * 4, int(counts[t]))
-
-    # ---- plan exactly like gen_data: targets, windows, gate, transforms
-    targets = vx.plan_targets(cfg, n_scans, poses)
-    specs, window_points = [], 0
-    for tgt in targets:
-        pb, pe, qb, qe = vx.window(n_scans, cfg.pod.priorScans, cfg.pod.pastScans, int(tgt))
-        pts = np.uint32(counts[qb:qe].sum(dtype=np.uint32))
-        labc = np.uint32(labelled[qb:qe].sum(dtype=np.uint32))
-        if not (np.float32(100.0) * np.float32(labc) / np.float32(pts) > 0):
-            continue  # "skipped."
-        anchor = poses[pe - 1]
-        ap_p, _ = vx.frame_transforms(anchor, poses[pb:pe])
-        ap_q, ep = vx.frame_transforms(anchor, poses[qb:qe])
-        specs.append(vx.FrameSpec(np.arange(pb, pe, dtype=np.uint32), ap_p, np.arange(qb, qe, dtype=np.uint32), ap_q, ep))
-        window_points += int(counts[pb:pe].sum()) + int(counts[qb:qe].sum())
+    specs, spec_targets, window_points = plan_frames(vx, cfg, n_scans, poses, seq)
     n_frames = len(specs)
     descs_dev, keep1 = be.build_descs(specs, None)  # outputs stay in HBM
+    spec_points = [int(seq.counts[s.prior_ids].sum()) + int(seq.counts[s.past_ids].sum()) for s in specs]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
 
     def timed(fn, steps):
         barrier()
@@ -270,15 +461,12 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - w0
-        dev_ms = e0.elapsed_time(e1)
-        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = reduce_max(e0.elapsed_time(e1), wall * 1e3)
         barrier()
-        return float(t[0]), float(t[1])
+        return dev_ms, wall_ms
 
     # ---- value: inputs resident in HBM
-    upload_all()
+    seq.upload(be)
     step_dev = lambda: be.process_descs(descs_dev, n_frames)
     for _ in range(args.warmup):
         step_dev()
@@ -297,12 +485,14 @@ def run_ours(args):
         total_frames = int(tf)
     value = total_frames / (ms_per_step / 1e3)
 
-    # ---- e2e: host buffers, H2D of every scan and D2H of every output inside the timed region
-    e2e = None
+    # ---- e2e: host buffers, H2D of every scan and D2H of every output inside the timed region.  Steps are submitted
+    # asynchronously and the scans of step k+1 are uploaded (under a second id range) while step k is traversed.
+    e2e, parity_check = None, None
     ring = None
+    per = be.label_bytes + 3 * be.packed_bytes
     if not args.no_e2e:
         try:
-            ring = vx.PinnedBuffer(n_frames * (be.label_bytes + 3 * be.packed_bytes))
+            ring = vx.PinnedBuffer(n_frames * per)
         except Exception as exc:  # the number is optional, the run is not
             sys.stderr.write(f"bench: no pinned output ring ({exc}); e2e skipped\n")
         if world > 1:  # the timed loop is collective: every rank measures e2e, or none does
@@ -311,27 +501,70 @@ def run_ours(args):
             if int(ok) == 0:
                 ring = None
     if ring is not None:
-        per = be.label_bytes + 3 * be.packed_bytes
-        outs = []
-        for k in range(n_frames):
-            base = ring.array[k * per:(k + 1) * per]
-            outs.append(dict(label=base[: be.label_bytes], bin=base[be.label_bytes: be.label_bytes + be.packed_bytes],
-                             occluded=base[be.label_bytes + be.packed_bytes: be.label_bytes + 2 * be.packed_bytes],
-                             invalid=base[be.label_bytes + 2 * be.packed_bytes:]))
-        descs_host, keep2 = be.build_descs(specs, outs)
+        outs = output_views(ring, be, n_frames)
+        ID2 = 1 << 20  # second id range
+        sets = []
+        for off in (0, ID2):
+            sp = [vx.FrameSpec(s.prior_ids + off, s.ap_prior, s.past_ids + off, s.ap_past, s.endpoints) for s in specs] if off else specs
+            sets.append(be.build_descs(sp, outs))
+        state = {"k": 0, "ticket": None}
+
+        def evict_set(off):
+            for t in range(n_scans):
+                be.evict_scan(t + off)
 
         def step_e2e():
-            be.evict_all()
-            upload_all()
-            be.process_descs(descs_host, n_frames)
+            k = state["k"]
+            cur, nxt = (0, ID2) if k % 2 == 0 else (ID2, 0)
+            if state["ticket"] is None:        # first step: nothing in flight yet, its scans go up now
+                seq.upload(be, id_offset=cur)
+            ticket = be.submit_descs(sets[k % 2][0], n_frames)
+            evict_set(nxt)                      # the job that read them was awaited at the end of the previous step
+            seq.upload(be, id_offset=nxt)       # step k+1's inputs cross PCIe while step k runs
+            be.wait(ticket)
+            state["ticket"] = ticket
+            state["k"] = k + 1
 
-        step_e2e()
+        be.evict_all()
+        step_e2e()                              # warm-up (also pins down the first-step special case)
         e_dev_ms, e_wall_ms = timed(step_e2e, max(1, args.steps))
-        e_ms = e_wall_ms / max(1, args.steps)  # includes host-side staging gaps
-        h2d = int(counts.sum()) * 20 + sum((len(s.prior_ids) + len(s.past_ids)) * (64 + 24) + len(s.endpoints) * 12 for s in specs)
+        be.sync()
+        e_ms = e_wall_ms / max(1, args.steps)   # wall clock: includes every host-side gap
+        h2d = int(seq.counts.sum()) * 20 + sum((len(s.prior_ids) + len(s.past_ids)) * (64 + 24) + len(s.endpoints) * 12 for s in specs)
         d2h = n_frames * per
         e2e = {"value": total_frames / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "ms_per_step": e_ms, "device_ms_per_step": e_dev_ms / max(1, args.steps)}
+               "ms_per_step": e_ms, "device_ms_per_step": e_dev_ms / max(1, args.steps),
+               "how": "vx_submit_frames / vx_wait; the next step's scans are uploaded (second id range) while this step is traversed"}
+        # ---- parity of the benchmarked workload: the frames the reference arm computed, byte for byte
+        if ref_line and ref_line.get("frame_hashes"):
+            index = {t: i for i, t in enumerate(spec_targets)}
+            mismatches, files, bad = 0, 0, []
+            for tgt, hashes in ref_line["frame_hashes"].items():
+                i = index.get(int(tgt))
+                if i is None:
+                    continue
+                mine = frame_digest(outs[i])
+                for ext, h in hashes.items():
+                    files += 1
+                    if mine[ext] != h:
+                        mismatches += 1
+                        bad.append(f"{int(tgt):06d}.{ext}")
+            parity_check = {"oracle": "ref" if cpu_baseline and cpu_baseline.get("kind") == "reference" else "port",
+                            "frames": files // 4, "files": files, "mismatches": mismatches,
+                            "what": "sha256 of the e2e step's host outputs vs the files the cpu_baseline leg wrote for the same targets"}
+            if mismatches:
+                parity_check["first_bad"] = bad[:8]
+        be.evict_all()
+        seq.upload(be)                          # back to the plain id range for what follows
+
+    # ---- optional legs, outside the headline's timed regions
+    extra_configs, strong = None, None
+    if not args.no_extra:
+        budget_left = lambda: args.time_budget - (time.perf_counter() - t_start)
+        if world == 1 and rank == 0:
+            extra_configs = run_extra_configs(vx, torch, args, seq, poses, n_scans, local_rank, ref_line, budget_left)
+        elif world > 1:
+            strong = run_strong(vx, torch, dist, args, rank, world, local_rank, host_threads, seq, ring, per)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -342,11 +575,13 @@ def run_ours(args):
         fill_gbs = fill_bytes / fill_s / 1e9 if fill_s > 0 else 0.0
         ivp_bytes = fill_bytes + st["frames"] * (2.0 * nvox + 3.0 * nvox / 8.0)  # SURVEY.md 8(d) B_frame
         ivp_s = (st["fill_ms"] + st["vote_ms"] + st["emit_ms"] + st["pack_ms"]) / 1e3
+        traffic = fill_traffic_factor()
+        vis_s = st["visibility_ms"] / 1e3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32",
             "data": "synthetic",
-            "config": {"workload": f"{args.config}.cfg on a synthetic {n_scans}-scan sequence per GPU (seq-00 shape, ~{int(counts.mean())} pts/scan): "
+            "config": {"workload": f"{args.config}.cfg on a synthetic {n_scans}-scan sequence per GPU (seq-00 shape, ~{int(seq.counts.mean())} pts/scan): "
                                    f"{n_frames} target frames per step per GPU, window up to {cfg.pod.pastScans + 1} scans",
                        "frames_per_step_per_gpu": n_frames, "frames_in_flight": be.frames_in_flight,
                        "l2_policy": "inputs larger than L2 (window of one frame = 180 MB, sequence = 11.6 GB)",
@@ -357,27 +592,213 @@ def run_ours(args):
             "stage_ms_per_step": {k: st[k] / args.steps for k in ("fill_ms", "vote_ms", "emit_ms", "visibility_ms", "pack_ms", "total_ms")},
             "roofline": {"bound": "hbm", "kernel": "vx_fill_kernel (K1+K2: transform, filter, key, histogram insert)",
                          "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak,
-                         # dram bytes per launch: the ncu --set full capture in profiles/ measured 0.142 x the algorithmic
-                         # bytes (a scan tile is loaded once and inserted into every frame of the launch that uses it)
-                         "traffic": 0.142 * fill_bytes / max(1, launches["fill_launches"]),
-                         "traffic_source": "profiles/r01_ncu_full_fill_final.txt (dram__bytes_read+write / algorithmic bytes of that launch)",
+                         # DRAM bytes per launch are NOT measured by this run: they are the algorithmic bytes of this run's launches
+                         # times the dram/algorithmic ratio of the tracked ncu capture named in traffic_source
+                         "traffic": traffic["factor"] * fill_bytes / max(1, launches["fill_launches"]) if traffic["factor"] else None,
+                         "traffic_source": traffic["source"],
                          "peak_source": peak_src, "bytes_per_launch": fill_bytes / max(1, launches["fill_launches"]),
+                         # algorithmic bytes of each fill launch of one step, in launch order (one launch per 128 frames)
+                         "bytes_of_launch": [20 * sum(spec_points[a:a + 128]) for a in range(0, n_frames, 128)],
                          "ms_per_launch": st["fill_ms"] / max(1, launches["fill_launches"]),
                          "insert_vote_pack": {"achieved": ivp_bytes / ivp_s / 1e9 if ivp_s > 0 else 0.0,
                                               "frac": (ivp_bytes / ivp_s / 1e9 / peak) if ivp_s > 0 else 0.0,
                                               "bytes_per_frame": ivp_bytes / max(1, st["frames"])}},
             "traversal": {"kernel": "vx_visibility_kernel (K4)", "rays_per_frame": st["rays_cast"] / max(1, st["frames"]),
                           "dda_steps_per_frame": st["dda_steps"] / max(1, st["frames"]),
-                          "gsteps_per_s": st["dda_steps"] / (st["visibility_ms"] / 1e3) / 1e9 if st["visibility_ms"] > 0 else 0.0},
+                          "gsteps_per_s": st["dda_steps"] / vis_s / 1e9 if vis_s > 0 else 0.0,
+                          "waves_per_frame": st["vis_waves"] / max(1, st["frames"]),
+                          "cycles_per_wave": {k: st["vis_cycles"][i] / max(1, st["vis_waves"]) for i, k in enumerate(("snapshot", "resolve", "trace", "apply"))}},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
+            "parity_check": parity_check,
+            "extra_configs": extra_configs,
+            "strong": strong,
             "clocks": sampler.summary(),
-            "setup_s": {"generate": t_gen},
+            "setup_s": {"generate": t_gen, "total_wall": time.perf_counter() - t_start},
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity_check and parity_check["mismatches"]:
+        sys.stderr.write(f"bench: PARITY MISMATCH against the reference: {parity_check}\n")
+        return 3
     return 0
+
+
+def fill_traffic_factor():
+    """dram bytes / algorithmic bytes of vx_fill_kernel from the newest tracked ncu summary that states both (profiles/
+    r*_fill_traffic.json: written by tools/fill_traffic.py from an `ncu --set full` capture and the launch it names)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(pdir)):
+        if f.endswith("_fill_traffic.json"):
+            best = f
+    if best:
+        try:
+            d = json.load(open(os.path.join(pdir, best)))
+            return {"factor": float(d["dram_bytes"]) / float(d["algorithmic_bytes"]), "source": f"profiles/{best}: {d.get('launch', '')}"}
+        except Exception:
+            pass
+    return {"factor": 0.142, "source": "profiles/r01_ncu_full_fill_final.txt (dram__bytes_read+write / algorithmic bytes of the launch it names; "
+                                       "a stored ratio, not measured by this run)"}
+
+
+def run_extra_configs(vx, torch, args, seq, poses, n_scans, device, ref_line, budget_left):
+    """BASELINE configs[2..4] on one GPU, each with a reference sample beside it (N = 1 only)."""
+    out = {}
+    profile = (ref_line or {}).get("pass_profile_s") or []
+    cases = [
+        ("dense", "semantic_kitti_dense", dict(first=0, frames=600), "configs[2]: stride-1 windows (same per-frame work as configs[1])"),
+        ("stress_512", "stress_512", dict(first=0, frames=40), "configs[3]: 512x512x64 @ 0.1 m, 200 scans -> 40 frames"),
+        ("past1000", "past1000", dict(first=0, frames=2), "configs[4]: 1001-scan windows, 1000 updateInvalid passes per frame"),
+    ]
+    for name, cfg_name, sel, what in cases:
+        if budget_left() < 60:
+            out[name] = {"skipped": "time budget", "workload": what}
+            continue
+        t_case = time.perf_counter()
+        cfg = vx.Config(cfg_file(cfg_name))
+        targets = vx.plan_targets(cfg, n_scans, poses)[sel["first"]: sel["first"] + sel["frames"]]
+        last_scan = min(n_scans, int(targets[-1]) + cfg.pod.pastScans + 1)
+        be = vx.Backend.from_config(cfg, device=device, stream=torch.cuda.current_stream().cuda_stream, frames_in_flight=len(targets))
+        seq.upload(be, 0, last_scan)
+        specs, kept, pts = plan_frames(vx, cfg, n_scans, poses, seq, targets=targets)
+        descs, keep = be.build_descs(specs, None)
+        be.process_descs(descs, min(2, len(specs)))          # warm-up: allocations, first-touch
+        be.reset_stage_times()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        be.process_descs(descs, len(specs))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        st = be.stage_times()
+        rec = {"workload": what, "config": cfg_name + ".cfg", "frames": len(specs), "grid": list(be.size), "ms": ms,
+               "value": len(specs) / (ms / 1e3), "unit": UNIT, "passes_per_frame": int(np.mean([len(s.endpoints) for s in specs])),
+               "stage_ms": {k: st[k] for k in ("fill_ms", "vote_ms", "emit_ms", "visibility_ms", "pack_ms")},
+               "seconds_per_frame_in_flight": ms / 1e3}
+        be.close()
+        # reference sample beside it
+        try:
+            if name == "dense" and ref_line:
+                c = ref_line["cpu_baseline"]
+                rec["reference"] = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
+                                    "sample": "the cpu_baseline sample of the headline: dense frames are the same full 71-scan windows"}
+            elif budget_left() > 90:
+                n_passes = rec["passes_per_frame"]
+                k = 6
+                r = reference_subprocess(cfg_name, ["--ref-frames", "2", "--ref-cores", "2", "--ref-passes", str(k)], timeout=max(60, int(budget_left())))
+                r["profile"] = profile
+                sec = reference_estimate(r, n_passes)
+                cores = (ref_line or {}).get("cpu_baseline", {}).get("cores") or (os.cpu_count() or 1)
+                rec["reference"] = {"seconds_per_frame_one_core": sec, "value_all_cores_extrapolated": cores / sec, "unit": UNIT, "cores": cores,
+                                    "kind": r["cpu_baseline"]["kind"],
+                                    "sample": f"2 frames on 2 processes: clear + fill + updateOcclusions x2 + the first {k} of {n_passes} updateInvalid passes + "
+                                              f"save timed; the other passes EXTRAPOLATED with the per-pass cost profile of complete configs[1] frames; "
+                                              f"all-cores figure = cores / seconds per frame (assumes the linear scaling the headline sample shows)",
+                                    "stage_s_per_frame": r["stage_s_per_frame"]}
+            else:
+                rec["reference"] = {"skipped": "time budget"}
+        except Exception as e:
+            rec["reference"] = {"failed": str(e)[:200]}
+        rec["wall_s"] = time.perf_counter() - t_case
+        out[name] = rec
+    return out
+
+
+def run_strong(vx, torch, dist, args, rank, world, device, host_threads, seq0, ring, per):
+    """BASELINE configs[2] / [3] as the north star splits them: ONE seed-1234 sequence, contiguous ranges of its target
+    list per rank plus the window halo, scans uploaded from pinned host memory, outputs into host memory and hashed;
+    rank 0 then runs the whole job alone and the digests are compared."""
+    result = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, cfg_name, n_scans, max_targets in (("dense", "semantic_kitti_dense", args.scans, None), ("stress_512", "stress_512", 271, 40)):
+        cfg = vx.Config(cfg_file(cfg_name))
+        params = vx.synth_params(seed=1234)
+        poses = vx.synth_velo_poses(params, n_scans).astype(np.float32)
+        targets = vx.plan_targets(cfg, n_scans, poses)
+        if max_targets:
+            targets = targets[:max_targets]
+        total = len(targets)
+        lo, hi = total * rank // world, total * (rank + 1) // world      # gen_data_pipeline.cpp's --shard i/n split
+        mine = targets[lo:hi]
+        be = vx.Backend.from_config(cfg, device=device, stream=stream, frames_in_flight=min(total, 1036))
+        per_c = be.label_bytes + 3 * be.packed_bytes
+        chunk = max(1, min(len(mine) if len(mine) else 1, ring.nbytes // per_c)) if ring is not None else 0
+        if ring is None or chunk == 0:
+            result[name] = {"skipped": "no pinned output ring"}
+            be.close()
+            continue
+
+        def shard_job(tg, backend):
+            first = int(tg[0]) - cfg.pod.priorScans if len(tg) else 0
+            first = max(0, first)
+            last = min(n_scans, int(tg[-1]) + cfg.pod.pastScans + 1) if len(tg) else 0
+            if rank == 0 and name == "dense" and seq0.n >= last:
+                s, own = seq0, False                                     # rank 0's headline sequence IS seed 1234
+            else:
+                s, own = Sequence(vx, 1234, first, last - first, host_threads), True
+            specs, kept, _ = plan_frames(vx, cfg, n_scans, poses, s, targets=tg)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s.upload(backend, first, last)                               # pinned host -> HBM: part of the timed job
+            busy, digests = run_host_job(vx, backend, s, specs, ring, max(1, min(len(specs), ring.nbytes // per_c)))
+            backend.sync()
+            wall = time.perf_counter() - t0
+            backend.evict_all()
+            if own:
+                s.free()
+            return busy, wall, digests, kept, last - first
+
+        # (the digests are computed inside run_host_job between chunks; `busy` excludes them, `wall` does not)
+        busy, wall, digests, kept, scans_read = shard_job(mine, be)
+        t = torch.tensor([busy], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_n = float(t)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (kept, [d.hex() for d in digests], scans_read))
+        rec = None
+        if rank == 0:
+            busy1, wall1, digests1, kept1, _ = shard_job_single(vx, be, cfg, n_scans, poses, targets, ring, per_c, seq0 if name == "dense" else None,
+                                                               host_threads)
+            sharded = {}
+            for kept_r, dig_r, _ in gathered:
+                sharded.update(dict(zip(kept_r, dig_r)))
+            single = dict(zip(kept1, [d.hex() for d in digests1]))
+            equal = sharded == single
+            rec = {"workload": f"{cfg_name}.cfg, ONE seed-1234 sequence of {n_scans} scans, {total} targets in {world} contiguous ranges + window halo",
+                   "frames": total, "n_gpus": world, "seconds": t_n, "value": total / t_n, "unit": UNIT,
+                   "single_gpu_seconds": busy1, "single_gpu_value": total / busy1, "speedup": busy1 / t_n,
+                   "files_equal": bool(equal), "files_compared": 4 * len(single),
+                   "scans_read_per_rank": [g[2] for g in gathered],
+                   "timing": "max over ranks of the wall time between vx_submit_frames and vx_wait (uploads from pinned host memory and "
+                             "copies into pinned host memory included; hashing excluded); the single-GPU run is timed the same way on rank 0"}
+        dist.barrier()
+        be.close()
+        if rank == 0:
+            result[name] = rec
+    return result if rank == 0 else None
+
+
+def shard_job_single(vx, be, cfg, n_scans, poses, targets, ring, per_c, seq0, host_threads):
+    """The whole job on this rank alone (rank 0, while the others wait at the barrier)."""
+    first = max(0, int(targets[0]) - cfg.pod.priorScans)
+    last = min(n_scans, int(targets[-1]) + cfg.pod.pastScans + 1)
+    if seq0 is not None and seq0.n >= last:
+        s, own = seq0, False
+    else:
+        s, own = Sequence(vx, 1234, first, last - first, host_threads), True
+    specs, kept, _ = plan_frames(vx, cfg, n_scans, poses, s, targets=targets)
+    t0 = time.perf_counter()
+    s.upload(be, first, last)
+    busy, digests = run_host_job(vx, be, s, specs, ring, max(1, min(len(specs), ring.nbytes // per_c)))
+    be.sync()
+    wall = time.perf_counter() - t0
+    be.evict_all()
+    if own:
+        s.free()
+    return busy, wall, digests, kept, last - first
 
 
 def main():

@@ -17,7 +17,8 @@
  * Conventions: every entry point returns 0 on success or a negative vx_status; CUDA failures are
  * reported, never papered over -- there is NO CPU fallback.  Matrices are 16 floats, column-major
  * (Eigen::Matrix4f storage order).  The caller owns all host buffers; the library owns all device
- * memory.  One context per GPU; calls on one context must be serialised by the caller.
+ * memory.  One context per GPU; calls on one context must be serialised by the caller (one thread at a
+ * time; the library's own worker thread behind vx_submit_frames is synchronised inside).
  * All outputs are byte-identical to the files the reference writes.
  */
 #ifndef VOXELIZER_B200_H_
@@ -159,10 +160,20 @@ int vx_upload_wait(vx_ctx* ctx, uint64_t ticket);
 int vx_evict_scan(vx_ctx* ctx, uint32_t scan_id);
 int vx_evict_all(vx_ctx* ctx);
 
-/* Runs n frames (any n; processed in batches of frames_in_flight).  Asynchronous with respect to the
- * host only until the outputs of the last batch are being copied; returns after all outputs landed. */
+/* Runs n frames (any n; processed in batches of frames_in_flight) and returns after all outputs landed:
+ * vx_submit_frames followed by vx_wait. */
 int vx_process_frames(vx_ctx* ctx, const vx_frame_desc* frames, uint32_t n);
-int vx_sync(vx_ctx* ctx);
+
+/* Asynchronous form (vx_submit_frame -> ticket -> vx_wait).  vx_submit_frames copies the descriptors and
+ * the id / matrix / endpoint arrays they point to and returns at once; a worker thread of the context runs the jobs in
+ * submission order.  Until vx_wait(ticket) has returned the caller must leave the job's OUTPUT buffers alone and must
+ * not evict or re-upload a scan id the job reads; uploading OTHER scans meanwhile is the point of this call (the next
+ * sequence crosses PCIe while this one is traversed).  vx_wait returns the job's status (its message through
+ * vx_last_error); ticket 0 waits for everything submitted so far and returns the first failure.  vx_last_error,
+ * vx_stage_times_get and vx_debug_dump describe finished jobs only: call them after vx_wait. */
+int vx_submit_frames(vx_ctx* ctx, const vx_frame_desc* frames, uint32_t n, uint64_t* ticket);
+int vx_wait(vx_ctx* ctx, uint64_t ticket);
+int vx_sync(vx_ctx* ctx); /* every job, every upload, the stream */
 
 int vx_stage_times_get(vx_ctx* ctx, vx_stage_times* out);
 int vx_stage_times_reset(vx_ctx* ctx);
@@ -178,6 +189,14 @@ typedef enum vx_dump_kind {
   VX_DUMP_INVALID = 4      /* uint8 per voxel, isInvalid                           */
 } vx_dump_kind;
 int vx_debug_dump(vx_ctx* ctx, uint32_t frame_index, int kind, void* dst, uint64_t* count);
+
+/* VoxelGrid::occludedBy(i, j, k, endpoint, visited*) as the PUBLIC method (VoxelGrid.h:89-90, VoxelGrid.cpp:235-316) on the
+ * occupancy of frame `frame_index` of the last finished job (same restriction as vx_debug_dump): one ray from the centre
+ * of voxel (i,j,k) towards `endpoint`.  *occluder = the reference-internal index i + j*Sx + k*Sx*Sy of the occupied voxel
+ * that stops it, or -1; visited_ijk receives up to visited_capacity (i,j,k) triples of the cells the reference loop looks
+ * at, in order (the occupied one included), *n_visited their full number.  visited_ijk / n_visited may be NULL. */
+int vx_trace_ray(vx_ctx* ctx, uint32_t frame_index, int32_t i, int32_t j, int32_t k, const float* endpoint, int32_t* visited_ijk,
+                 uint32_t visited_capacity, uint32_t* n_visited, int32_t* occluder);
 
 #ifdef __cplusplus
 }

@@ -103,6 +103,9 @@ class Oracle:
         f("fill").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         f("update_occlusions").argtypes = [C.c_void_p]
         f("update_invalid").argtypes = [C.c_void_p, C.c_void_p]
+        f("insert_occlusion_labels").argtypes = [C.c_void_p]
+        f("occluded_by").restype = C.c_int32
+        f("occluded_by").argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         f("grid_dump").restype = C.c_uint64
         f("grid_dump").argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         f("grid_counts").argtypes = [C.c_void_p, C.c_void_p]
@@ -268,6 +271,18 @@ class OracleGrid:
     def update_invalid(self, endpoint):
         e = _f32(endpoint).reshape(3)
         self.o._fn("update_invalid")(self.h, _ptr(e))
+
+    def insert_occlusion_labels(self):
+        """VoxelGrid::insertOcclusionLabels (VoxelGrid.cpp:75-96)."""
+        self.o._fn("insert_occlusion_labels")(self.h)
+
+    def occluded_by(self, i: int, j: int, k: int, endpoint, capacity: int = 4096):
+        """VoxelGrid::occludedBy(i, j, k, endpoint, &visited): (occluder internal index or -1, visited [n,3])."""
+        e = _f32(endpoint).reshape(3)
+        vis = np.zeros((capacity, 3), np.int32)
+        n = C.c_uint32()
+        r = self.o._fn("occluded_by")(self.h, i, j, k, _ptr(e), _ptr(vis), capacity, C.byref(n))
+        return int(r), vis[: min(int(n.value), capacity)].copy()
 
     def dump(self, what: str):
         code = {"occlusions": 0, "invalid": 1, "memo": 2}[what]

@@ -155,9 +155,11 @@ static std::string trim_spaces(const std::string& s) {
   return s.substr(b, e - b);
 }
 
-// rv::split with keep_empty_tokens: every delimiter closes a token; "" -> [""].
+// rv::split with keep_empty_tokens: every delimiter closes a token; an empty string has NO token
+// (boost token_iterator::initialize is never valid on an empty range).
 static std::vector<std::string> split_keep(const std::string& s, const std::string& delims) {
   std::vector<std::string> out;
+  if (s.empty()) return out;
   std::string cur;
   for (char ch : s) {
     if (delims.find(ch) != std::string::npos) {
@@ -378,7 +380,8 @@ struct Grid {
   }
 
   // VoxelGrid.cpp:235-316.  Returns hit voxel index or -1; memoises into `memo`.
-  int32_t cast(int32_t i, int32_t j, int32_t k, const float* e, std::vector<uint32_t>& path) {
+  int32_t cast(int32_t i, int32_t j, int32_t k, const float* e, std::vector<uint32_t>& path, std::vector<int32_t>* visited = nullptr) {
+    if (visited) visited->clear();  // VoxelGrid.cpp:243
     int32_t pos[3] = {i, j, k};
     const int32_t dim[3] = {nx, ny, nz};
     float tmax[3], tdelta[3];
@@ -406,6 +409,7 @@ struct Grid {
       if (pos[0] < 0 || pos[1] < 0 || pos[2] < 0) break;
       if (pos[0] >= nx || pos[1] >= ny || pos[2] >= nz) break;
       const int32_t v = idx(pos[0], pos[1], pos[2]);
+      if (visited) visited->insert(visited->end(), {pos[0], pos[1], pos[2]});  // VoxelGrid.cpp:291
       if (count[size_t(v)] > 0) {
         for (uint32_t t : path) memo[t] = v;
         return v;
@@ -462,6 +466,34 @@ struct Grid {
       if (memo[size_t(v)] == -2) memo[size_t(v)] = cast(i, j, k, e, path);
       inval[size_t(v)] = std::min(inval[size_t(v)], memo[size_t(v)]);
     });
+  }
+
+  // VoxelGrid.cpp:75-96: every voxel that was not occupied when the occlusions were computed takes count and labels of
+  // the first occupied voxel above it, if only occluded empty voxels lie between ("find label from above").
+  void fill_from_above() {
+    if (!occl_valid) occlusion_pass();
+    for (int32_t i = 0; i < nx; ++i)
+      for (int32_t j = 0; j < ny; ++j)
+        for (int32_t k = 0; k < nz; ++k) {
+          const int32_t g = idx(i, j, k);
+          if (occl[size_t(g)] == g) continue;
+          int32_t n = 1;
+          while (k + n < nz && occluded(i, j, k + n) && count[size_t(idx(i, j, k + n))] == 0) n += 1;
+          if (k + n < nz && count[size_t(idx(i, j, k + n))] > 0) {
+            const int32_t src = idx(i, j, k + n);
+            if (count[size_t(g)] == 0) touched.push_back(uint32_t(g));
+            count[size_t(g)] = count[size_t(src)];
+            // labels = labels of the source voxel (a map assignment: what the voxel held before is dropped)
+            std::vector<uint64_t> drop;
+            for (const auto& kv : hist)
+              if (uint32_t(kv.first >> 32) == uint32_t(g)) drop.push_back(kv.first);
+            for (uint64_t key : drop) hist.erase(key);
+            std::vector<std::pair<uint64_t, uint32_t>> add;
+            for (const auto& kv : hist)
+              if (uint32_t(kv.first >> 32) == uint32_t(src)) add.emplace_back((uint64_t(uint32_t(g)) << 32) | (kv.first & 0xFFFFFFFFu), kv.second);
+            for (const auto& kv : add) hist[kv.first] = kv.second;
+          }
+        }
   }
 
   bool occluded(int32_t i, int32_t j, int32_t k) const { return occl[size_t(idx(i, j, k))] > -1; }  // :65
@@ -961,6 +993,19 @@ void orc_fill(void* gp, void* cfgp, const float* anchor16, uint32_t nscans, cons
   orc::fill(anchor, ptrs, g, *static_cast<orc::Settings*>(cfgp));
 }
 void orc_update_occlusions(void* gp) { static_cast<orc::Grid*>(gp)->occlusion_pass(); }
+void orc_insert_occlusion_labels(void* gp) { static_cast<orc::Grid*>(gp)->fill_from_above(); }
+// VoxelGrid::occludedBy as a public call: returns the occluder (internal index) or -1; visited = (i,j,k) triples
+int32_t orc_occluded_by(void* gp, int32_t i, int32_t j, int32_t k, const float* e3, int32_t* visited, uint32_t capacity, uint32_t* n_visited) {
+  orc::Grid& g = *static_cast<orc::Grid*>(gp);
+  std::vector<uint32_t> path;
+  std::vector<int32_t> seen;
+  const int32_t r = g.cast(i, j, k, e3, path, &seen);
+  const uint32_t n = uint32_t(seen.size() / 3);
+  if (n_visited) *n_visited = n;
+  for (uint32_t q = 0; q < n && q < capacity; ++q)
+    for (int a = 0; a < 3; ++a) visited[3 * q + uint32_t(a)] = seen[3 * q + uint32_t(a)];
+  return r;
+}
 void orc_update_invalid(void* gp, const float* e3) { static_cast<orc::Grid*>(gp)->invalid_pass(e3); }
 uint64_t orc_grid_dump(void* gp, int what, int32_t* out) {
   const orc::Grid& g = *static_cast<orc::Grid*>(gp);

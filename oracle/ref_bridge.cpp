@@ -169,6 +169,16 @@ void vxref_fill(void* gp, void* cfgp, const float* anchor16, uint32_t nscans, co
 }
 
 void vxref_update_occlusions(void* gp) { static_cast<RefGrid*>(gp)->updateOcclusions(); }
+void vxref_insert_occlusion_labels(void* gp) { static_cast<RefGrid*>(gp)->insertOcclusionLabels(); }
+// VoxelGrid::occludedBy as the public method (VoxelGrid.h:89-90)
+int32_t vxref_occluded_by(void* gp, int32_t i, int32_t j, int32_t k, const float* e3, int32_t* visited, uint32_t capacity, uint32_t* n_visited) {
+  std::vector<Eigen::Vector3i> seen;
+  const int32_t r = static_cast<RefGrid*>(gp)->occludedBy(i, j, k, Eigen::Vector3f(e3[0], e3[1], e3[2]), &seen);
+  if (n_visited) *n_visited = uint32_t(seen.size());
+  for (uint32_t q = 0; q < seen.size() && q < capacity; ++q)
+    for (int a = 0; a < 3; ++a) visited[3 * q + uint32_t(a)] = seen[q][a];
+  return r;
+}
 
 void vxref_update_invalid(void* gp, const float* e3) {
   static_cast<RefGrid*>(gp)->updateInvalid(Eigen::Vector3f(e3[0], e3[1], e3[2]));

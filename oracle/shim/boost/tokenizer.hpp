@@ -2,7 +2,8 @@
 // boost::char_separator<char> + boost::tokenizer<char_separator<char>> over a std::string,
 // as used by the reference's rv::split (src/rv/string_utils.cpp:41-51).  Restated semantics
 // of char_separator with no kept delimiters:
-//   keep_empty_tokens: every dropped delimiter ends a token; "" -> [""], "a:" -> ["a",""],
+//   keep_empty_tokens: every dropped delimiter ends a token; "" -> [] (token_iterator::initialize
+//                      is never valid on an empty range), "a:" -> ["a",""],
 //                      ":a" -> ["","a"], "a::b" -> ["a","","b"].
 //   drop_empty_tokens: maximal runs of non-delimiter characters.
 #ifndef VXB200_ORACLE_BOOST_TOKENIZER_SHIM
@@ -30,6 +31,7 @@ class tokenizer {
   typedef std::vector<std::string>::const_iterator iterator;
   tokenizer(const std::string& s, const Sep& sep) {
     std::string cur;
+    if (s.empty()) return;
     if (sep.policy_ == keep_empty_tokens) {
       for (size_t i = 0; i < s.size(); ++i) {
         if (sep.dropped_.find(s[i]) != std::string::npos) {

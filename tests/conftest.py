@@ -6,6 +6,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def pytest_configure(config):
@@ -26,4 +28,6 @@ def _native_libraries():
     hdr = os.path.join(ROOT, "voxelizer_b200", "csrc", "vx_dda.h")
     if not os.path.exists(model) or os.path.getmtime(model) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", src, "-o", model])
+    from util import build_callers
+    build_callers()  # tests/callers: reference-shaped callers of the kept host API (links libvxhost.so)
     yield

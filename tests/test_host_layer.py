@@ -25,6 +25,12 @@ def test_parse_configuration_corners(port, tmp_path):
         p.write_text(random_cfg_text(rng))
         assert vx.Config(str(p)).as_dict() == port.load_config(str(p)).as_dict()
     assert vx.Config(str(tmp_path / "nope.cfg")).as_dict() == port.load_config(str(tmp_path / "nope.cfg")).as_dict()
+    # empty lists: boost::tokenizer yields no token for an empty range, so both keys are no-ops in the reference
+    empty = tmp_path / "empty_lists.cfg"
+    empty.write_text("voxel size: 0.5\nignore: []\njoin: []\npast scans: 3\n")
+    d = vx.Config(str(empty)).as_dict()
+    assert d == port.load_config(str(empty)).as_dict()
+    assert d["filtered"] == [] and d["join_pairs"] == [] and d["pastScans"] == 3
     bad = tmp_path / "bad.cfg"
     bad.write_text("max range: 7 0\n")
     with pytest.raises(vx.VxError):

@@ -26,7 +26,8 @@ C_ABI_SYMBOLS = (
     "vx_last_global_error", "vx_last_error", "vx_device_count", "vx_create", "vx_destroy", "vx_grid_info_get",
     "vx_frames_in_flight", "vx_host_alloc", "vx_host_free", "vx_upload_scan", "vx_upload_ticket", "vx_upload_wait",
     "vx_evict_scan", "vx_evict_all",
-    "vx_process_frames", "vx_sync", "vx_stage_times_get", "vx_stage_times_reset", "vx_debug_dump",
+    "vx_process_frames", "vx_submit_frames", "vx_wait", "vx_sync", "vx_stage_times_get", "vx_stage_times_reset",
+    "vx_debug_dump", "vx_trace_ray",
 )
 
 VX_OK = 0
@@ -143,6 +144,10 @@ def cuda_lib():
         L.vx_evict_scan.argtypes = [C.c_void_p, C.c_uint32]
         L.vx_evict_all.argtypes = [C.c_void_p]
         L.vx_process_frames.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_uint32]
+        L.vx_submit_frames.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_uint32, C.POINTER(C.c_uint64)]
+        L.vx_wait.argtypes = [C.c_void_p, C.c_uint64]
+        L.vx_trace_ray.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                   C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
         L.vx_sync.argtypes = [C.c_void_p]
         L.vx_stage_times_get.argtypes = [C.c_void_p, C.POINTER(StageTimes)]
         L.vx_stage_times_reset.argtypes = [C.c_void_p]
@@ -181,10 +186,6 @@ def host_lib():
         L.vxh_gen_data.restype = C.c_int
         L.vxh_gen_data.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(GenDataStats)]
-        L.vxh_gen_data_facade.restype = C.c_int
-        L.vxh_gen_data_facade.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int64, C.POINTER(C.c_uint64)]
-        L.vxh_facade_probe.restype = C.c_int
-        L.vxh_facade_probe.argtypes = [C.c_int, C.c_float] + [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_uint32] + [C.c_void_p] * 8
         _host = L
     return _host
 
@@ -352,42 +353,6 @@ def gen_data(cfg_path: str, seq_dir: str, out_dir: str, device: int = 0, shard=(
 # ------------------------------------------------------------------------------------------------------
 # The CUDA backend through the C ABI
 # ------------------------------------------------------------------------------------------------------
-def gen_data_facade(cfg_path: str, seq_dir: str, out_dir: str, device: int = 0, max_frames: int = -1) -> int:
-    """gen_data written against the kept reference API (VoxelGrid / fillVoxelGrid / saveVoxelGrid facade,
-    host/gen_data_facade.cpp), one frame at a time.  Returns the number of frames written."""
-    H = host_lib()
-    os.makedirs(out_dir, exist_ok=True)
-    n = C.c_uint64(0)
-    if H.vxh_gen_data_facade(cfg_path.encode(), seq_dir.encode(), out_dir.encode(), device, max_frames, C.byref(n)) != 0:
-        raise VxError(H.vxh_last_error().decode())
-    return int(n.value)
-
-
-def facade_probe(resolution, min_extent, max_extent, points4, labels, endpoints, device: int = 0) -> dict:
-    """vxb::VoxelGrid used directly (raw insert, updateOcclusions, updateInvalid, every per-voxel query).
-    Arrays come back in the reference's internal index order i + j*Sx + k*Sx*Sy."""
-    H = host_lib()
-    pts = _f32(points4).reshape(-1, 4)
-    lab = _u32(labels)
-    ep = _f32(endpoints).reshape(-1, 3)
-    mn, mx = _f32(list(min_extent)[:3]), _f32(list(max_extent)[:3])
-    size = np.zeros(3, np.uint32)
-    off = np.zeros(3, np.float32)
-    # sizes first (needs the grid): probe once with no points to learn them
-    be = Backend(resolution, list(min_extent)[:3], list(max_extent)[:3], 0.0, float("inf"), hidecar=False, device=device, frames_in_flight=1)
-    nv = be.nvox
-    be.close()
-    out = {k: np.zeros(nv, np.uint8) for k in ("occluded", "free", "invalid")}
-    out.update({k: np.zeros(nv, np.uint32) for k in ("count", "n_labels", "majority")})
-    rc = H.vxh_facade_probe(device, C.c_float(resolution), _p(mn), _p(mx), _p(pts), _p(lab), len(lab), _p(ep), len(ep), _p(size), _p(off),
-                            _p(out["occluded"]), _p(out["free"]), _p(out["invalid"]), _p(out["count"]), _p(out["n_labels"]), _p(out["majority"]))
-    if rc != 0:
-        raise VxError(H.vxh_last_error().decode())
-    out["size"] = tuple(int(x) for x in size)
-    out["offset"] = off
-    return out
-
-
 @dataclass
 class FrameSpec:
     prior_ids: np.ndarray
@@ -517,6 +482,30 @@ class Backend:
 
     def process_descs(self, arr, n):
         self._check(cuda_lib().vx_process_frames(self._ctx, arr, n), "vx_process_frames")
+
+    def submit_descs(self, arr, n) -> int:
+        """Asynchronous: returns a ticket for wait(); scans with other ids may be uploaded meanwhile."""
+        t = C.c_uint64()
+        self._check(cuda_lib().vx_submit_frames(self._ctx, arr, n, C.byref(t)), "vx_submit_frames")
+        return int(t.value)
+
+    def wait(self, ticket: int = 0):
+        self._check(cuda_lib().vx_wait(self._ctx, ticket), "vx_wait")
+
+    def sync(self):
+        self._check(cuda_lib().vx_sync(self._ctx), "vx_sync")
+
+    def evict_scan(self, scan_id: int):
+        cuda_lib().vx_evict_scan(self._ctx, scan_id)
+
+    def trace_ray(self, frame_index: int, i: int, j: int, k: int, endpoint, capacity: int = 4096):
+        """VoxelGrid::occludedBy(i, j, k, endpoint, &visited) on frame `frame_index` of the last job:
+        (occluder as reference-internal index or -1, visited [n,3] int32)."""
+        e = _f32(endpoint).reshape(3)
+        vis = np.zeros((capacity, 3), np.int32)
+        n, occ = C.c_uint32(), C.c_int32()
+        self._check(cuda_lib().vx_trace_ray(self._ctx, frame_index, i, j, k, _p(e), _p(vis), capacity, C.byref(n), C.byref(occ)), "vx_trace_ray")
+        return int(occ.value), vis[: min(int(n.value), capacity)].copy()
 
     def stage_times(self) -> dict:
         st = StageTimes()

@@ -6,11 +6,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/voxelizer_b200.h"
 #include "vx_launch.h"
@@ -53,7 +60,25 @@ struct ScratchMem {
 enum { EV_BEGIN = 0, EV_VIS_BEGIN, EV_VIS, EV_PACK, EV_END, EV_COUNT };
 
 // per-slot counter block (uint32 words): used/overflow of both tables, then two 64-bit statistics
-constexpr size_t kCounterWords = 4 + 2 * VX_SLOT_STATS + 2;  // 24 words = 96 bytes per slot
+constexpr size_t kCounterWords = 4 + 2 * VX_SLOT_STATS + 2;  // 32 words = 128 bytes per slot
+
+// One asynchronous vx_submit_frames call: the descriptors and every array they point to are copied, so the
+// caller's memory is free again when the call returns (the OUTPUT buffers are the caller's until vx_wait).
+struct Job {
+  uint64_t ticket = 0;
+  std::vector<vx_frame_desc> frames;
+  std::vector<uint32_t> ids;
+  std::vector<float> ap, ep;
+  int rc = 0;
+  std::string error;
+};
+
+thread_local std::string* tl_error_sink = nullptr;  // set on the worker thread: errors belong to the job, not the context
+
+struct NvtxRange {  // per-stage ranges on the host side of a batch (Stopwatch tic/toc -> NVTX)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 }  // namespace
 
@@ -71,6 +96,7 @@ struct vx_ctx {
   uint32_t* d_reject_bits = nullptr;
 
   std::unordered_map<uint32_t, DeviceScan> scans;
+  cudaMemPool_t scan_pool = nullptr;  // private stream-ordered pool of the scan cache
 
   uint32_t max_slots = 0;   // frames per batch (one visibility launch)
   uint32_t table_sets = 0;  // frames per fill -> vote -> emit launch
@@ -105,12 +131,24 @@ struct vx_ctx {
   vx_stage_times times{};
   uint32_t last_batch = 0;
   std::string error;
+
+  // Asynchronous jobs (vx_submit_frames / vx_wait): one worker thread runs them in submission order.  `mu` guards
+  // what the worker shares with the caller's upload / evict calls: the scan map, the upload marks and counters.
+  std::mutex mu;
+  std::mutex qmu;
+  std::condition_variable qcv, dcv;
+  std::deque<std::unique_ptr<Job>> queue;
+  std::map<uint64_t, std::pair<int, std::string>> failed;  // tickets that did not end with VX_OK
+  uint64_t next_ticket = 1, finished_ticket = 0;
+  bool stop = false;
+  std::thread worker;
 };
 
 namespace {
 
 int fail(vx_ctx* c, int code, const std::string& msg) {
-  if (c) c->error = msg;
+  if (tl_error_sink) *tl_error_sink = msg;
+  else if (c) c->error = msg;
   else g_global_error = msg;
   return code;
 }
@@ -318,7 +356,14 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   rc = ensure_scratch(c, nb);
   if (rc != VX_OK) return rc;
 
-  // ---- stage the batch description
+  // ---- stage the batch description (the scan map and the upload marks are shared with the caller's thread)
+  NvtxRange nvtx_batch("vx:batch");
+  nvtxRangePushA("vx:stage+enqueue");
+  std::unique_lock<std::mutex> lk(c->mu);
+  struct PopOnExit {
+    bool armed = true;
+    ~PopOnExit() { if (armed) nvtxRangePop(); }
+  } nvtx_enqueue;
   size_t n_items = 0, n_ap = 0, n_ep = 0;
   for (uint32_t f = 0; f < nb; ++f) {
     n_items += frames[f].n_prior + frames[f].n_past;
@@ -447,6 +492,10 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS], st));
   VX_CUDA(c, vx_launch_pack(c->d_slots, nb, c->nvox, st));
   VX_CUDA(c, cudaEventRecord(c->ev[EV_PACK], st));
+  lk.unlock();  // everything that reads the scan cache is enqueued; uploads / evictions of OTHER scans may go on
+  nvtx_enqueue.armed = false;
+  nvtxRangePop();
+  NvtxRange nvtx_copy("vx:copy_out+wait");
 
   // Copy-out.  Everything above is enqueued by now: a copy into pageable memory blocks the host, never the device.
   // `.label` / `.bin` are final after a group's emit: they leave on the copy stream while the rays are traced.
@@ -546,6 +595,64 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   return VX_OK;
 }
 
+void evict_locked(vx_ctx* c, uint32_t scan_id) {
+  const auto it = c->scans.find(scan_id);
+  if (it == c->scans.end()) return;
+  if (it->second.points) cudaFreeAsync(it->second.points, c->copy_in);
+  if (it->second.labels) cudaFreeAsync(it->second.labels, c->copy_in);
+  c->scans.erase(it);
+}
+
+// All frames of one call, in batches of equal size (a short last batch would leave most of the device idle for
+// a whole batch time).  Runs on the worker thread.
+int process_job(vx_ctx* c, const vx_frame_desc* frames, uint32_t n) {
+  VX_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t n_batches = n ? (n + c->max_slots - 1) / c->max_slots : 0;
+  const uint32_t per_batch = n_batches ? (n + n_batches - 1) / n_batches : 0;
+  for (uint32_t base = 0; base < n;) {
+    uint32_t nb = n - base < per_batch ? n - base : per_batch;
+    if (nb > c->max_slots) nb = c->max_slots;
+    int rc = run_batch(c, frames + base, nb);
+    if (rc == VX_ERR_TABLE_OVERFLOW) {
+      // grow the histogram tables (x4) and redo this batch
+      if (c->log2_target >= 28) return fail(c, VX_ERR_TABLE_OVERFLOW, "histogram table overflow at 2^28 slots");
+      VX_CUDA(c, cudaStreamSynchronize(c->stream));
+      free_slots(c);
+      c->log2_target += 2;
+      c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
+      size_t free_b = 0, total_b = 0;
+      VX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+      while (c->table_sets > 1 && (size_t)c->table_sets * table_set_bytes(c) > free_b / 2) c->table_sets /= 2;
+      continue;
+    }
+    if (rc != VX_OK) return rc;
+    base += nb;
+  }
+  return VX_OK;
+}
+
+void worker_main(vx_ctx* c) {
+  for (;;) {
+    std::unique_ptr<Job> job;
+    {
+      std::unique_lock<std::mutex> lk(c->qmu);
+      c->qcv.wait(lk, [&] { return c->stop || !c->queue.empty(); });
+      if (c->queue.empty()) return;  // stop requested and nothing left to run
+      job = std::move(c->queue.front());
+      c->queue.pop_front();
+    }
+    tl_error_sink = &job->error;
+    job->rc = process_job(c, job->frames.data(), (uint32_t)job->frames.size());
+    tl_error_sink = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(c->qmu);
+      if (job->rc != VX_OK) c->failed[job->ticket] = std::make_pair(job->rc, job->error);
+      c->finished_ticket = job->ticket;
+    }
+    c->dcv.notify_all();
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -605,11 +712,16 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
   VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
   VX_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_copy_out, cudaEventDisableTiming));
-  {  // scans live in the device's stream-ordered memory pool; keep freed blocks for the next upload
-    cudaMemPool_t pool;
-    VX_CREATE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  {  // scans live in a stream-ordered memory pool OF THIS CONTEXT (the device's default pool belongs to the embedding
+     // application); freed blocks are kept for the next upload and returned to the driver by vx_destroy
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    VX_CREATE_CUDA(cudaMemPoolCreate(&c->scan_pool, &props));
     uint64_t keep = UINT64_MAX;
-    VX_CREATE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    VX_CREATE_CUDA(cudaMemPoolSetAttribute(c->scan_pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   VX_CREATE_CUDA(vx_visibility_prepare());
 
@@ -672,12 +784,15 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   uint32_t want = options && options->frames_in_flight ? options->frames_in_flight : 4u * resident;
   if (c->keep_tables && want > 8u && !(options && options->frames_in_flight)) want = 8u;  // debug: small batches,
   if (c->keep_tables || want < c->table_sets) c->table_sets = want;                       // every frame its own tables
-  {
-    const size_t fixed = (size_t)resident * scratch_bytes(c) + (size_t)c->table_sets * table_set_bytes(c);
+  {  // the largest batch whose frame records, histogram tables and traversal scratch fit into 70 % of the free memory
+     // (scratch: one buffer per RESIDENT CTA, at most one per frame; tables: one set per frame of a fill group)
     const size_t budget = free_b / 10 * 7;
-    const size_t left = budget > fixed ? budget - fixed : 0;
-    const size_t fit = left / frame_bytes(c);
-    if ((size_t)want > fit) want = (uint32_t)fit;
+    auto cost = [&](uint32_t n) {
+      const size_t n_scratch = n < resident ? n : resident;
+      const size_t n_sets = n < c->table_sets ? n : c->table_sets;
+      return n_scratch * scratch_bytes(c) + n_sets * table_set_bytes(c) + (size_t)n * frame_bytes(c);
+    };
+    while (want > 1 && cost(want) > budget) want = want - (want + 3) / 4;
   }
   if (want > 65535u) want = 65535u;
   if (want < 1) want = 1;
@@ -693,6 +808,14 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
 
 void vx_destroy(vx_ctx* c) {
   if (!c) return;
+  if (c->worker.joinable()) {  // pending jobs are finished first
+    {
+      std::lock_guard<std::mutex> lk(c->qmu);
+      c->stop = true;
+    }
+    c->qcv.notify_all();
+    c->worker.join();
+  }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_in) cudaStreamSynchronize(c->copy_in);
@@ -702,6 +825,7 @@ void vx_destroy(vx_ctx* c) {
     if (kv.second.labels) cudaFreeAsync(kv.second.labels, c->copy_in);
   }
   if (c->copy_in) cudaStreamSynchronize(c->copy_in);
+  if (c->scan_pool) cudaMemPoolDestroy(c->scan_pool);
   for (const UploadMark& m : c->marks) cudaEventDestroy(m.ev);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->ev_copy_out) cudaEventDestroy(c->ev_copy_out);
@@ -743,15 +867,16 @@ uint32_t vx_frames_in_flight(const vx_ctx* c) { return c ? c->max_slots : 0; }
 int vx_upload_scan(vx_ctx* c, uint32_t scan_id, const float* xyzr, const uint32_t* labels, uint32_t n) {
   if (!c || (n && (!xyzr || !labels))) return fail(c, VX_ERR_INVALID, "null argument");
   VX_CUDA(c, cudaSetDevice(c->device));
-  vx_evict_scan(c, scan_id);
+  std::lock_guard<std::mutex> lk(c->mu);
+  evict_locked(c, scan_id);
   DeviceScan s;
   s.n = n;
   if (n) {
-    // stream-ordered pool allocation on the upload stream: no device-wide synchronisation per scan.  No kernel
-    // is pending when this is called (vx_process_frames returns after its batch), so blocks freed by an evict
-    // can be handed out again at once.
-    VX_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&s.points), (size_t)n * sizeof(float4), c->copy_in));
-    VX_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&s.labels), (size_t)n * sizeof(uint32_t), c->copy_in));
+    // stream-ordered pool allocation on the upload stream: no device-wide synchronisation per scan.  A block freed
+    // by an evict is handed out again at once: the caller must not evict a scan that a submitted, not yet awaited
+    // job reads (include/voxelizer_b200.h).
+    VX_CUDA(c, cudaMallocFromPoolAsync(reinterpret_cast<void**>(&s.points), (size_t)n * sizeof(float4), c->scan_pool, c->copy_in));
+    VX_CUDA(c, cudaMallocFromPoolAsync(reinterpret_cast<void**>(&s.labels), (size_t)n * sizeof(uint32_t), c->scan_pool, c->copy_in));
     VX_CUDA(c, cudaMemcpyAsync(s.points, xyzr, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->copy_in));
     VX_CUDA(c, cudaMemcpyAsync(s.labels, labels, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_in));
     s.seq = ++c->upload_seq;
@@ -764,38 +889,46 @@ int vx_upload_scan(vx_ctx* c, uint32_t scan_id, const float* xyzr, const uint32_
   return VX_OK;
 }
 
-uint64_t vx_upload_ticket(const vx_ctx* c) { return c ? c->upload_seq : 0; }
+uint64_t vx_upload_ticket(const vx_ctx* c) {
+  if (!c) return 0;
+  std::lock_guard<std::mutex> lk(const_cast<vx_ctx*>(c)->mu);
+  return c->upload_seq;
+}
 
 int vx_upload_wait(vx_ctx* c, uint64_t ticket) {
   if (!c) return VX_ERR_INVALID;
-  if (ticket > c->upload_seq) ticket = c->upload_seq;
-  if (ticket <= c->done_seq) return VX_OK;
-  VX_CUDA(c, cudaSetDevice(c->device));
-  if (ticket > c->marked_seq) {
-    const int rc = mark_uploads(c);
-    if (rc != VX_OK) return rc;
-  }
-  for (const UploadMark& m : c->marks)
-    if (m.seq >= ticket) {
-      VX_CUDA(c, cudaEventSynchronize(m.ev));
-      break;
+  cudaEvent_t ev = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (ticket > c->upload_seq) ticket = c->upload_seq;
+    if (ticket <= c->done_seq) return VX_OK;
+    VX_CUDA(c, cudaSetDevice(c->device));
+    if (ticket > c->marked_seq) {
+      const int rc = mark_uploads(c);
+      if (rc != VX_OK) return rc;
     }
+    for (const UploadMark& m : c->marks)
+      if (m.seq >= ticket) {
+        ev = m.ev;
+        break;
+      }
+  }
+  if (ev) VX_CUDA(c, cudaEventSynchronize(ev));  // (unlocked: a job may be enqueueing meanwhile)
+  std::lock_guard<std::mutex> lk(c->mu);
   prune_marks(c);
   return VX_OK;
 }
 
 int vx_evict_scan(vx_ctx* c, uint32_t scan_id) {
   if (!c) return VX_ERR_INVALID;
-  const auto it = c->scans.find(scan_id);
-  if (it == c->scans.end()) return VX_OK;
-  if (it->second.points) cudaFreeAsync(it->second.points, c->copy_in);
-  if (it->second.labels) cudaFreeAsync(it->second.labels, c->copy_in);
-  c->scans.erase(it);
+  std::lock_guard<std::mutex> lk(c->mu);
+  evict_locked(c, scan_id);
   return VX_OK;
 }
 
 int vx_evict_all(vx_ctx* c) {
   if (!c) return VX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
   for (auto& kv : c->scans) {
     if (kv.second.points) cudaFreeAsync(kv.second.points, c->copy_in);
     if (kv.second.labels) cudaFreeAsync(kv.second.labels, c->copy_in);
@@ -804,41 +937,87 @@ int vx_evict_all(vx_ctx* c) {
   return VX_OK;
 }
 
+int vx_submit_frames(vx_ctx* c, const vx_frame_desc* frames, uint32_t n, uint64_t* ticket) {
+  if (!c || (n && !frames) || !ticket) return fail(c, VX_ERR_INVALID, "null argument");
+  std::unique_ptr<Job> job(new Job);
+  job->frames.assign(frames, frames + n);
+  size_t n_ids = 0, n_ap = 0, n_ep = 0;
+  for (uint32_t f = 0; f < n; ++f) {
+    const vx_frame_desc& fr = frames[f];
+    if ((fr.n_prior && (!fr.prior_ids || !fr.ap_prior)) || (fr.n_past && (!fr.past_ids || !fr.ap_past)) || (fr.n_endpoints && !fr.endpoints))
+      return fail(c, VX_ERR_INVALID, "frame descriptor has null arrays");
+    n_ids += fr.n_prior + fr.n_past;
+    n_ap += fr.n_prior + fr.n_past;
+    n_ep += fr.n_endpoints;
+  }
+  job->ids.resize(n_ids);
+  job->ap.resize(n_ap * 16);
+  job->ep.resize(n_ep * 3);
+  size_t ii = 0, ai = 0, ei = 0;
+  for (uint32_t f = 0; f < n; ++f) {  // (the vectors never grow again: the pointers below stay valid)
+    vx_frame_desc& fr = job->frames[f];
+    auto take_ids = [&](const uint32_t*& p, uint32_t k) {
+      if (k) std::memcpy(&job->ids[ii], p, (size_t)k * 4);
+      p = k ? &job->ids[ii] : nullptr;
+      ii += k;
+    };
+    auto take_ap = [&](const float*& p, uint32_t k) {
+      if (k) std::memcpy(&job->ap[ai * 16], p, (size_t)k * 64);
+      p = k ? &job->ap[ai * 16] : nullptr;
+      ai += k;
+    };
+    take_ids(fr.prior_ids, fr.n_prior);
+    take_ap(fr.ap_prior, fr.n_prior);
+    take_ids(fr.past_ids, fr.n_past);
+    take_ap(fr.ap_past, fr.n_past);
+    if (fr.n_endpoints) std::memcpy(&job->ep[ei * 3], fr.endpoints, (size_t)fr.n_endpoints * 12);
+    fr.endpoints = fr.n_endpoints ? &job->ep[ei * 3] : nullptr;
+    ei += fr.n_endpoints;
+  }
+  {
+    std::lock_guard<std::mutex> lk(c->qmu);
+    if (!c->worker.joinable()) c->worker = std::thread(worker_main, c);
+    job->ticket = c->next_ticket++;
+    *ticket = job->ticket;
+    c->queue.push_back(std::move(job));
+  }
+  c->qcv.notify_one();
+  return VX_OK;
+}
+
+int vx_wait(vx_ctx* c, uint64_t ticket) {
+  if (!c) return VX_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(c->qmu);
+  if (ticket == 0 || ticket >= c->next_ticket) ticket = c->next_ticket - 1;  // 0 = everything submitted so far
+  c->dcv.wait(lk, [&] { return c->finished_ticket >= ticket; });
+  int rc = VX_OK;
+  for (auto it = c->failed.begin(); it != c->failed.end() && it->first <= ticket;) {  // the first failure up to `ticket`
+    if (rc == VX_OK) {
+      rc = it->second.first;
+      c->error = it->second.second;
+    }
+    it = c->failed.erase(it);
+  }
+  return rc;
+}
+
 int vx_process_frames(vx_ctx* c, const vx_frame_desc* frames, uint32_t n) {
   if (!c || (n && !frames)) return fail(c, VX_ERR_INVALID, "null argument");
-  VX_CUDA(c, cudaSetDevice(c->device));
-  // batches of equal size (a short last batch would leave most of the device idle for a whole batch time)
-  const uint32_t n_batches = n ? (n + c->max_slots - 1) / c->max_slots : 0;
-  const uint32_t per_batch = n_batches ? (n + n_batches - 1) / n_batches : 0;
-  for (uint32_t base = 0; base < n;) {
-    uint32_t nb = n - base < per_batch ? n - base : per_batch;
-    if (nb > c->max_slots) nb = c->max_slots;
-    int rc = run_batch(c, frames + base, nb);
-    if (rc == VX_ERR_TABLE_OVERFLOW) {
-      // grow the histogram tables (x4) and redo this batch
-      if (c->log2_target >= 28) return fail(c, VX_ERR_TABLE_OVERFLOW, "histogram table overflow at 2^28 slots");
-      VX_CUDA(c, cudaStreamSynchronize(c->stream));
-      free_slots(c);
-      c->log2_target += 2;
-      c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
-      size_t free_b = 0, total_b = 0;
-      VX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-      while (c->table_sets > 1 && (size_t)c->table_sets * table_set_bytes(c) > free_b / 2) c->table_sets /= 2;
-      continue;
-    }
-    if (rc != VX_OK) return rc;
-    base += nb;
-  }
-  return VX_OK;
+  uint64_t ticket = 0;
+  const int rc = vx_submit_frames(c, frames, n, &ticket);
+  if (rc != VX_OK) return rc;
+  return vx_wait(c, ticket);
 }
 
 int vx_sync(vx_ctx* c) {
   if (!c) return VX_ERR_INVALID;
+  const int rc = vx_wait(c, 0);
   VX_CUDA(c, cudaSetDevice(c->device));
   VX_CUDA(c, cudaStreamSynchronize(c->copy_in));
   VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::lock_guard<std::mutex> lk(c->mu);
   prune_marks(c);
-  return VX_OK;
+  return rc;
 }
 
 int vx_stage_times_get(vx_ctx* c, vx_stage_times* out) {
@@ -850,6 +1029,28 @@ int vx_stage_times_get(vx_ctx* c, vx_stage_times* out) {
 int vx_stage_times_reset(vx_ctx* c) {
   if (!c) return VX_ERR_INVALID;
   c->times = vx_stage_times{};
+  return VX_OK;
+}
+
+int vx_trace_ray(vx_ctx* c, uint32_t frame_index, int32_t i, int32_t j, int32_t k, const float* endpoint, int32_t* visited_ijk,
+                 uint32_t visited_capacity, uint32_t* n_visited, int32_t* occluder) {
+  if (!c || !endpoint || !occluder || (visited_capacity && !visited_ijk)) return fail(c, VX_ERR_INVALID, "null argument");
+  if (frame_index >= c->last_batch) return fail(c, VX_ERR_INVALID, "frame index outside the last batch");
+  VX_CUDA(c, cudaSetDevice(c->device));
+  int32_t* d_buf = nullptr;
+  const size_t words = 2 + (size_t)visited_capacity * 3;
+  VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&d_buf), words * 4));
+  std::vector<int32_t> host(words);
+  cudaError_t e = vx_launch_trace_ray(c->slots[frame_index].dev.occ, c->geom, i, j, k, endpoint, d_buf + 2, visited_capacity, d_buf, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), d_buf, words * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_buf);
+  if (e != cudaSuccess) return fail(c, VX_ERR_CUDA, std::string("vx_trace_ray: ") + cudaGetErrorString(e));
+  const uint32_t n = (uint32_t)host[0];
+  if (n_visited) *n_visited = n;
+  *occluder = host[1];
+  const uint32_t keep = n < visited_capacity ? n : visited_capacity;
+  if (keep) std::memcpy(visited_ijk, host.data() + 2, (size_t)keep * 12);
   return VX_OK;
 }
 

@@ -178,8 +178,8 @@ vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict
       d.log2_i = s.input.log2_cap;
       d.both = use.both;
       // Where can the tile land in this frame?  centre' +- |R| * half-extent bounds every transformed point (NaN
-      // coordinates never enter fminf / fmaxf and are rejected per point anyway).  One metre of slack dwarfs any
-      // rounding difference between this bound and the per-point arithmetic.
+      // coordinates never enter fminf / fmaxf and are rejected per point anyway).  One metre of slack plus 1e-5 of the
+      // operands' magnitude dwarfs any rounding difference between this bound and the per-point arithmetic.
       float lo[3], hi[3];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -198,7 +198,11 @@ vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const float centre = m[0 * 4 + r] * cx + m[1 * 4 + r] * cy + m[2 * 4 + r] * cz + m[3 * 4 + r];
-        const float reach = fabsf(m[0 * 4 + r]) * hx + fabsf(m[1 * 4 + r]) * hy + fabsf(m[2 * 4 + r]) * hz + 1.0f;
+        // the slack grows with the magnitude of the operands: beyond ~1.6e7 one ulp exceeds a fixed metre (a config may
+        // allow such points: max range 1e9), and a tile of near points that holds one far point must not be dropped
+        const float mag = fabsf(m[0 * 4 + r]) * (fabsf(cx) + hx) + fabsf(m[1 * 4 + r]) * (fabsf(cy) + hy) +
+                          fabsf(m[2 * 4 + r]) * (fabsf(cz) + hz) + fabsf(m[3 * 4 + r]);
+        const float reach = fabsf(m[0 * 4 + r]) * hx + fabsf(m[1 * 4 + r]) * hy + fabsf(m[2 * 4 + r]) * hz + 1.0f + 1.0e-5f * mag;
         outside |= centre + reach < g.off[r] || centre - reach > g.off[r] + gsize[r];
       }
       d.skip = outside ? 1u : 0u;

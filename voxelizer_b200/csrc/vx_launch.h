@@ -27,6 +27,11 @@ cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, 
                                  uint32_t* locks, cudaStream_t stream);
 uint64_t vx_visibility_visits(VxGridGeom geom);  // visits per pass (must stay < 2^25)
 
+// VoxelGrid::occludedBy as a public call: one ray over a frame's occupancy; visited = capacity x (i, j, k), result = {cells
+// looked at, occluder (reference-internal index) or -1}.
+cudaError_t vx_launch_trace_ray(const uint32_t* occ, VxGridGeom geom, int32_t i, int32_t j, int32_t k, const float* endpoint,
+                                int32_t* visited, uint32_t capacity, int32_t* result, cudaStream_t stream);
+
 // K5b: occl / alive bitmaps -> MSB-first packed .occluded / .invalid.
 cudaError_t vx_launch_pack(const VxSlot* slots, uint32_t n_slots, uint64_t nvox, cudaStream_t stream);
 

@@ -833,7 +833,43 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
   }
 }
 
+// VoxelGrid::occludedBy(i, j, k, endpoint, visited*) as a PUBLIC call (VoxelGrid.h:89-90, VoxelGrid.cpp:235-316): one ray,
+// every cell the reference loop looks at (the occupied one that ends it included), and the reference-internal index
+// i + j * Sx + k * Sx * Sy of the occluder or -1.  The memo side effect of the reference is not observable through the
+// public API (both passes reset occludedBy_ before they read it), so there is none here.
+__global__ void vx_trace_ray_kernel(const uint32_t* __restrict__ occ, const VxGridGeom g, const int32_t i, const int32_t j,
+                                    const int32_t k, const float e0, const float e1, const float e2, int32_t* visited,
+                                    const uint32_t capacity, int32_t* result) {
+  VxRay r;
+  r.begin(g, i, j, k, e0, e1, e2);
+  uint32_t n = 0;
+  int32_t occluder = -1;
+  for (;;) {
+    if (!r.inside(g)) break;
+    if (n < capacity) {
+      visited[3u * n + 0u] = r.i;
+      visited[3u * n + 1u] = r.j;
+      visited[3u * n + 2u] = r.k;
+    }
+    ++n;
+    const uint32_t L = lin(g, r.i, r.j, r.k);
+    if ((occ[L >> 5] >> (L & 31u)) & 1u) {
+      occluder = r.i + r.j * g.nx + r.k * g.nx * g.ny;
+      break;
+    }
+    if (!r.advance()) break;
+  }
+  result[0] = (int32_t)n;
+  result[1] = occluder;
+}
+
 }  // namespace
+
+cudaError_t vx_launch_trace_ray(const uint32_t* occ, VxGridGeom geom, int32_t i, int32_t j, int32_t k, const float* endpoint,
+                                int32_t* visited, uint32_t capacity, int32_t* result, cudaStream_t stream) {
+  vx_trace_ray_kernel<<<1, 1, 0, stream>>>(occ, geom, i, j, k, endpoint[0], endpoint[1], endpoint[2], visited, capacity, result);
+  return cudaGetLastError();
+}
 
 cudaError_t vx_visibility_prepare() {
   return cudaFuncSetAttribute(vx_visibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisShared));

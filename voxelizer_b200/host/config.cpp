@@ -20,6 +20,9 @@ std::string trim(const std::string& s) {
 }
 
 std::vector<std::string> split(const std::string& line, const std::string& delim) {
+  // boost::tokenizer yields NO token for an empty range (token_iterator::initialize: valid_ = begin != end ? ... : false);
+  // otherwise keep_empty_tokens closes a token at every delimiter ("a:" -> ["a", ""]).
+  if (line.empty()) return {};
   std::vector<std::string> tokens(1);
   for (const char ch : line) {
     if (delim.find(ch) == std::string::npos) tokens.back().push_back(ch);

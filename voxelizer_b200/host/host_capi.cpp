@@ -197,61 +197,4 @@ int vxh_gen_data(const char* cfg_path, const char* seq_dir, const char* out_dir,
   }
 }
 
-// gen_data written against VoxelGrid / fillVoxelGrid / saveVoxelGrid (host/gen_data_facade.cpp)
-int vxh_gen_data_facade(const char* cfg_path, const char* seq_dir, const char* out_dir, int device, int64_t max_frames, uint64_t* frames) {
-  std::string err;
-  try {
-    const vxb::Config cfg = vxb::parseConfiguration(cfg_path);
-    const int rc = vxb::runGenDataFacade(cfg, seq_dir, out_dir, device, max_frames, false, frames, &err);
-    if (rc != 0) g_error = err;
-    return rc;
-  } catch (const std::exception& e) {
-    g_error = e.what();
-    return -1;
-  }
-}
-
-// VoxelGrid used directly: raw insert() of n already transformed points, updateOcclusions(), one
-// updateInvalid() per endpoint, then every per-voxel query of the reference API.  Arrays are indexed by the
-// reference's internal index i + j*Sx + k*Sx*Sy.  size3 / offset3 may be null.
-int vxh_facade_probe(int device, float resolution, const float* min3, const float* max3, const float* points4, const uint32_t* labels,
-                     uint32_t n, const float* endpoints3, uint32_t n_endpoints, uint32_t* size3, float* offset3, uint8_t* occluded,
-                     uint8_t* is_free, uint8_t* invalid, uint32_t* counts, uint32_t* n_labels, uint32_t* majority) {
-  try {
-    vxb::VoxelGrid grid(device);
-    grid.initialize(resolution, vxb::Vector4f(min3[0], min3[1], min3[2], 1), vxb::Vector4f(max3[0], max3[1], max3[2], 1));
-    for (uint32_t p = 0; p < n; ++p)
-      grid.insert(vxb::Vector4f(points4[4 * p], points4[4 * p + 1], points4[4 * p + 2], points4[4 * p + 3]), labels[p]);
-    grid.updateOcclusions();
-    for (uint32_t e = 0; e < n_endpoints; ++e)
-      grid.updateInvalid(vxb::Vector3f(endpoints3[3 * e], endpoints3[3 * e + 1], endpoints3[3 * e + 2]));
-    if (size3)
-      for (int a = 0; a < 3; ++a) size3[a] = grid.size(uint32_t(a));
-    if (offset3)
-      for (int a = 0; a < 3; ++a) offset3[a] = grid.offset()[a];
-    for (uint32_t k = 0; k < grid.size(2); ++k)
-      for (uint32_t j = 0; j < grid.size(1); ++j)
-        for (uint32_t i = 0; i < grid.size(0); ++i) {
-          const size_t idx = size_t(grid.index(int32_t(i), int32_t(j), int32_t(k)));
-          occluded[idx] = grid.isOccluded(int32_t(i), int32_t(j), int32_t(k));
-          is_free[idx] = grid.isFree(int32_t(i), int32_t(j), int32_t(k));
-          invalid[idx] = grid.isInvalid(int32_t(i), int32_t(j), int32_t(k));
-          const vxb::VoxelGrid::Voxel& v = grid(i, j, k);
-          counts[idx] = v.count;
-          n_labels[idx] = uint32_t(v.labels.size());
-          uint32_t best = 0, bestc = 0;  // voxelize_utils.cpp:237-245
-          for (const auto& lc : v.labels)
-            if (lc.second > bestc) {
-              bestc = lc.second;
-              best = lc.first;
-            }
-          majority[idx] = best;
-        }
-    return 0;
-  } catch (const std::exception& e) {
-    g_error = e.what();
-    return -1;
-  }
-}
-
 }  // extern "C"

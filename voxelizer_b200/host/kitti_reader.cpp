@@ -169,7 +169,8 @@ void KittiReader::load(uint32_t t, Laserscan& scan, std::vector<uint32_t>& label
 
 namespace {
 
-// whole file into `dst` (at most `capacity` bytes); returns the file size, or -1 if it cannot be opened
+// whole file into `dst` (at most `capacity` bytes); returns the file size, or -1 if it cannot be opened.  A short
+// read (EIO, or the file shrank between fstat and read) throws: the tail of `dst` still holds an older scan.
 int64_t slurp(const std::string& filename, void* dst, size_t capacity) {
   const int fd = ::open(filename.c_str(), O_RDONLY);
   if (fd < 0) return -1;
@@ -186,6 +187,7 @@ int64_t slurp(const std::string& filename, void* dst, size_t capacity) {
     got += size_t(n);
   }
   ::close(fd);
+  if (got != want) throw std::runtime_error("short read: " + filename);
   return int64_t(st.st_size);
 }
 

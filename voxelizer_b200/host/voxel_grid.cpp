@@ -210,6 +210,22 @@ const std::vector<VoxelGrid::Voxel>& VoxelGrid::voxels() const {
   return voxels_;
 }
 
+int32_t VoxelGrid::occludedBy(int32_t i, int32_t j, int32_t k, const Vector3f& endpoint, std::vector<Vector3i>* visited) const {
+  flush();
+  const float e[3] = {endpoint[0], endpoint[1], endpoint[2]};
+  // a ray visits at most one voxel per step and every step moves one axis one way: Sx + Sy + Sz bounds the list
+  const uint32_t capacity = visited ? sizex_ + sizey_ + sizez_ + 1u : 0u;
+  std::vector<int32_t> ijk(size_t(capacity) * 3);
+  uint32_t n = 0;
+  int32_t occluder = -1;
+  if (vx_trace_ray(ctx_, 0, i, j, k, e, capacity ? ijk.data() : nullptr, capacity, &n, &occluder) != VX_OK) fail(ctx_, "vx_trace_ray");
+  if (visited) {
+    visited->clear();
+    for (uint32_t q = 0; q < n && q < capacity; ++q) visited->push_back(Vector3i(ijk[3 * q], ijk[3 * q + 1], ijk[3 * q + 2]));
+  }
+  return occluder;
+}
+
 bool VoxelGrid::isOccluded(int32_t i, int32_t j, int32_t k) const {
   flush();
   return occludedFlag_[(size_t(i) * sizey_ + size_t(j)) * sizez_ + size_t(k)] != 0;

@@ -19,9 +19,9 @@
 //     reference would let later passes see the new points; no caller does that).
 //   * insert() (raw, already transformed points) and fillVoxelGrid() (scan + pose + Config filters) cannot
 //     be mixed on one grid between two clear() calls: std::logic_error.
-//   * occludedBy() and insertOcclusionLabels() are not offered: the first is the traversal's internal,
-//     memo-writing helper (its effect is inside updateOcclusions / updateInvalid), the second is dead code
-//     in the reference (both call sites commented out: gen_data.cpp:108-109, Mainframe.cpp:303-304).
+//   * occludedBy() is the PUBLIC method (VoxelGrid.h:89-90): one ray on the device over the grid's occupancy, same
+//     return value and visited list; its memo side effect is not observable through the public API (both passes
+//     reset occludedBy_ before reading it) and does not exist here.
 #ifndef VOXELIZER_B200_HOST_VOXEL_GRID_H_
 #define VOXELIZER_B200_HOST_VOXEL_GRID_H_
 
@@ -73,6 +73,11 @@ class VoxelGrid {
 
   void updateOcclusions();
   void updateInvalid(const Vector3f& position);
+
+  /** ray from voxel (i,j,k) towards `endpoint`: index() of the occupied voxel that stops it or -1; `visited` receives
+   *  every voxel the ray looks at, the occluder included (VoxelGrid.h:89-90, VoxelGrid.cpp:235-316) */
+  int32_t occludedBy(int32_t i, int32_t j, int32_t k, const Vector3f& endpoint = Vector3f(0.0f, 0.0f, 0.0f),
+                     std::vector<Vector3i>* visited = nullptr) const;
 
   bool isOccluded(int32_t i, int32_t j, int32_t k) const;
   bool isFree(int32_t i, int32_t j, int32_t k) const;
@@ -138,10 +143,6 @@ void fillVoxelGrid(const Matrix4f& anchor_pose, const std::vector<PointcloudPtr>
 
 /** write <directory>/<basename>.bin ("input") or .label/.occluded/.invalid ("target") (voxelize_utils.cpp:218-296) */
 void saveVoxelGrid(const VoxelGrid& grid, const std::string& directory, const std::string& basename, const std::string& mode = "input");
-
-/** gen_data.cpp:46-142 on top of the API above, one frame at a time (tests / demonstration). */
-int runGenDataFacade(const Config& config, const std::string& sequences_dirname, const std::string& output_voxel_dirname, int device,
-                     int64_t maxFrames, bool verbose, uint64_t* framesWritten, std::string* error);
 
 }  // namespace vxb
 
