@@ -73,7 +73,10 @@ typedef struct vx_options {
   uint32_t debug;                /* 1: keep histogram tables after a batch for vx_debug_dump */
   uint32_t table_sets;           /* frames per fill -> vote -> emit launch; frames this far apart share one set of
                                     histogram tables (default 128) */
-  uint32_t reserved[2];
+  uint32_t vis_mode;             /* shape of the traversal kernel: 0 = chosen per batch (few frames: one 512-thread CTA per SM and
+                                    whole-face waves, short time per frame; many frames: 7 x 128-thread CTAs per SM, most frames per
+                                    second), 1 = always the many-frames shape, 2 = always the few-frames shape.  Same bytes either way. */
+  uint32_t reserved[1];
 } vx_options;
 
 /* One target frame = one iteration of gen_data.cpp:62-142 that passed the "labelled" gate.

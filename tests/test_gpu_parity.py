@@ -23,6 +23,13 @@ def orc(request):
     return Oracle(request.param)
 
 
+@pytest.fixture(params=[1, 2], ids=["throughput-shape", "latency-shape"])
+def vis_mode(request):
+    """Both shapes of the traversal kernel (vx_options.vis_mode): 7 x 128-thread CTAs per SM with waves of <= 1280 live cells,
+    and one 512-thread CTA per SM with whole-face waves.  Left to itself the library picks by batch size."""
+    return request.param
+
+
 def _load_sequence(seq):
     cnt, poses = vx.read_poses(seq)
     scans, labels = zip(*[load_scan(seq, t) for t in range(cnt)])
@@ -38,12 +45,12 @@ def _backend(cfg_name, scans, raw_labels, **kw):
 
 @pytest.mark.parametrize("cfg_name,n,beams,az", [("test_small", 10, 16, 300), ("example", 8, 32, 500), ("settings", 5, 32, 600),
                                                   ("semantic_kitti", 7, 64, 1200)])
-def test_frame_internals(orc, tmp_path, cfg_name, n, beams, az):
+def test_frame_internals(orc, tmp_path, cfg_name, n, beams, az, vis_mode):
     """histograms, majority labels, occupancy, occlusions_, invalid_ and the packed outputs of single frames."""
     seq = make_sequence(str(tmp_path / "seq"), n, beams, az)
     cnt, poses, scans, labels, raw = _load_sequence(seq)
     cfg = vx.Config(cfg_path(cfg_name))
-    be = _backend(cfg_name, scans, raw)
+    be = _backend(cfg_name, scans, raw, vis_mode=vis_mode)
     for target in (0, cnt // 2, cnt - 1):  # cnt-1: the last scan is its own past window (SURVEY.md A.5)
         pb, pe, qb, qe = vx.window(cnt, cfg.pod.priorScans, cfg.pod.pastScans, target)
         prior, past = list(range(pb, pe)), list(range(qb, qe))
@@ -55,7 +62,7 @@ def test_frame_internals(orc, tmp_path, cfg_name, n, beams, az):
     be.close()
 
 
-def test_adversarial_points(orc):
+def test_adversarial_points(orc, vis_mode):
     """Boundary ranges, voxel faces, NaN / inf, label ties, majority label 0, instance bits, empty scans."""
     cfg_name = "test_small"  # min range 2.5, max range 40, ignore [0, 30], join {0:[1]}, {10:[252,13]}; res 0.8
     rng = np.random.default_rng(1)
@@ -84,7 +91,7 @@ def test_adversarial_points(orc):
     shift = np.eye(4, dtype=np.float32)
     shift[:3, 3] = (1.25, -0.5, 0.1)
     poses = np.stack([ident, shift.T.reshape(16), ident])
-    be = _backend(cfg_name, scans, raw)
+    be = _backend(cfg_name, scans, raw, vis_mode=vis_mode)
     for prior, past in (([0], [1, 2]), ([0, 1], [2]), ([1], [1]), ([2], [])):
         o = oracle_frame(orc, cfg_path(cfg_name), scans, labels, poses, prior, past)
         p = product_frame(be, poses, prior, past)
@@ -92,12 +99,12 @@ def test_adversarial_points(orc):
     be.close()
 
 
-def test_endpoints_everywhere(orc, tmp_path):
+def test_endpoints_everywhere(orc, tmp_path, vis_mode):
     """updateInvalid with endpoints outside the grid, on voxel centres / faces / corners and at the origin."""
     seq = make_sequence(str(tmp_path / "seq"), 3, 32, 500)
     cnt, poses, scans, labels, raw = _load_sequence(seq)
     for cfg_name in ("example", "test_small"):
-        be = _backend(cfg_name, scans, raw)
+        be = _backend(cfg_name, scans, raw, vis_mode=vis_mode)
         res, off = float(be.resolution), be.offset.astype(np.float64)
         sx, sy, sz = be.size
         eps = [(0, 0, 0), (70, 3, 1), (-5, -30, 9), (1e4, 1e4, 1e4), tuple(off + res * np.array([3.5, 2.5, 1.5])), tuple(off + res * np.array([4, 4, 2])),
@@ -110,7 +117,7 @@ def test_endpoints_everywhere(orc, tmp_path):
         be.close()
 
 
-def test_random_occupancy_visibility(orc):
+def test_random_occupancy_visibility(orc, vis_mode):
     """Dense random occupancy on odd-sized grids: stresses in-wave resolution and the multi-word columns."""
     rng = np.random.default_rng(9)
     for (mn, mx, res), dens in ((((0, -4, -1), (8, 4, 1), 0.5), 0.2), (((-3, -2, -1), (5, 7, 2.5), 0.5), 0.05), (((0, -3, 0), (4, 3, 8), 1.0), 0.3),
@@ -120,7 +127,7 @@ def test_random_occupancy_visibility(orc):
         pts = np.column_stack([rng.uniform(mn[a], mx[a], n) for a in range(3)] + [np.zeros(n)]).astype(np.float32)
         lab = rng.integers(1, 5, n).astype(np.uint32)
         eps = np.column_stack([rng.uniform(mn[a] - 2, mx[a] + 2, 7) for a in range(3)]).astype(np.float32)
-        be = vx.Backend(res, mn, mx, 0.0, 1e9, hidecar=False, debug=True)
+        be = vx.Backend(res, mn, mx, 0.0, 1e9, hidecar=False, debug=True, vis_mode=vis_mode)
         be.upload_scan(0, pts, lab)
         ident = np.eye(4, dtype=np.float32).reshape(1, 16)
         spec = vx.FrameSpec(np.array([0], np.uint32), ident, np.zeros(0, np.uint32), np.zeros((0, 16), np.float32), eps)
@@ -199,12 +206,12 @@ def test_unknown_scan_is_an_error():
     be.close()
 
 
-def test_stress_grid_512(orc, tmp_path):
+def test_stress_grid_512(orc, tmp_path, vis_mode):
     """BASELINE configs[3]: 512 x 512 x 64 @ 0.1 m -- two 32-cell chunks per column, 16x16-voxel coarse blocks,
     16.8 M voxels.  Small scans and two invalid passes keep the oracle at a few seconds."""
     seq = make_sequence(str(tmp_path / "seq"), 3, 32, 700)
     cnt, poses, scans, labels, raw = _load_sequence(seq)
-    be = _backend("stress_512", scans, raw, frames_in_flight=1)
+    be = _backend("stress_512", scans, raw, frames_in_flight=1, vis_mode=vis_mode)
     assert be.size == (512, 512, 64)
     o = oracle_frame(orc, cfg_path("stress_512"), scans, labels, poses, [0], [1, 2])
     p = product_frame(be, poses, [0], [1, 2])
@@ -212,14 +219,14 @@ def test_stress_grid_512(orc, tmp_path):
     be.close()
 
 
-def test_more_passes_than_memo_epochs(orc, tmp_path):
+def test_more_passes_than_memo_epochs(orc, tmp_path, vis_mode):
     """BASELINE configs[4] in small: far more updateInvalid passes than the 127 pass tags of the memo, so the tag
     counter restarts (twice) inside one frame."""
     seq = make_sequence(str(tmp_path / "seq"), 3, 16, 300)
     cnt, poses, scans, labels, raw = _load_sequence(seq)
     rng = np.random.default_rng(3)
     eps = np.column_stack([rng.uniform(-2, 28, 300), rng.uniform(-14, 14, 300), rng.uniform(-2.5, 5, 300)]).astype(np.float32)
-    be = _backend("test_small", scans, raw)
+    be = _backend("test_small", scans, raw, vis_mode=vis_mode)
     o = oracle_frame(orc, cfg_path("test_small"), scans, labels, poses, [0], [1, 2], extra_endpoints=eps)
     p = product_frame(be, poses, [0], [1, 2], extra_endpoints=eps)
     assert_frames_equal(p, o)
@@ -272,12 +279,12 @@ def _synth_scans(n, seed=1234):
     return [xyzr[t, : counts[t]] for t in range(n)], [lab[t, : counts[t]] for t in range(n)], poses
 
 
-def test_full_window_frame_of_the_benchmark(orc):
+def test_full_window_frame_of_the_benchmark(orc, vis_mode):
     """One whole frame of BASELINE configs[1] exactly as bench.py runs it: semantic_kitti.cfg, 1 + 70 scans of
     ~124 k points (seed 1234, the bench's sequence), 70 updateInvalid passes -- every observable against the oracle."""
     scans, raw, poses = _synth_scans(71)
     labels = [l & 0xFFFF for l in raw]
-    be = _backend("semantic_kitti", scans, raw, frames_in_flight=2)
+    be = _backend("semantic_kitti", scans, raw, frames_in_flight=2, vis_mode=vis_mode)
     assert be.size == (256, 256, 32)
     prior, past = [0], list(range(1, 71))
     o = oracle_frame(orc, cfg_path("semantic_kitti"), scans, labels, poses, prior, past)
@@ -287,7 +294,7 @@ def test_full_window_frame_of_the_benchmark(orc):
     be.close()
 
 
-def test_last_frame_of_a_sequence_at_full_size(orc):
+def test_last_frame_of_a_sequence_at_full_size(orc, vis_mode):
     """KittiReader.cpp:99-100: for the last scan the past window is the scan itself -- it is inserted twice and
     updateInvalid runs once with its endpoint at the origin.  Full-size scans and grid."""
     scans, raw, poses = _synth_scans(6)
@@ -296,7 +303,7 @@ def test_last_frame_of_a_sequence_at_full_size(orc):
     n = len(scans)
     pb, pe, qb, qe = vx.window(n, cfg.pod.priorScans, cfg.pod.pastScans, n - 1)
     assert (pb, pe, qb, qe) == (n - 1, n, n - 1, n)
-    be = _backend("semantic_kitti", scans, raw, frames_in_flight=2)
+    be = _backend("semantic_kitti", scans, raw, frames_in_flight=2, vis_mode=vis_mode)
     o = oracle_frame(orc, cfg_path("semantic_kitti"), scans, labels, poses, [n - 1], [n - 1])
     p = product_frame(be, poses, [n - 1], [n - 1])
     assert np.array_equal(p["endpoints"], np.zeros((1, 3), np.float32)) or np.abs(p["endpoints"]).max() < 1e-6

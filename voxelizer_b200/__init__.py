@@ -52,7 +52,7 @@ class FilterDesc(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("frames_in_flight", C.c_uint32), ("table_log2_capacity", C.c_uint32), ("stream", C.c_void_p),
-                ("debug", C.c_uint32), ("table_sets", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+                ("debug", C.c_uint32), ("table_sets", C.c_uint32), ("vis_mode", C.c_uint32), ("reserved", C.c_uint32 * 1)]
 
 
 class FrameDesc(C.Structure):
@@ -385,7 +385,7 @@ class Backend:
 
     def __init__(self, resolution, min_extent, max_extent, min_range, max_range, hidecar=True, filtered=(), join_pairs=(),
                  device: int = 0, frames_in_flight: int = 0, table_log2_capacity: int = 0, debug: bool = False, stream: int = 0,
-                 table_sets: int = 0):
+                 table_sets: int = 0, vis_mode: int = 0):
         L = cuda_lib()
         gd = GridDesc(resolution=float(resolution))
         for a in range(3):
@@ -397,7 +397,7 @@ class Backend:
                         filtered_labels=self._filtered.ctypes.data if len(self._filtered) else None, n_filtered=len(self._filtered),
                         join_pairs=self._joins.ctypes.data if len(self._joins) else None, n_join_pairs=len(self._joins) // 2)
         op = Options(frames_in_flight=frames_in_flight, table_log2_capacity=table_log2_capacity, stream=stream or None,
-                     debug=1 if debug else 0, table_sets=table_sets)
+                     debug=1 if debug else 0, table_sets=table_sets, vis_mode=vis_mode)
         ctx = C.c_void_p()
         rc = L.vx_create(device, C.byref(gd), C.byref(fd), C.byref(op), C.byref(ctx))
         if rc != VX_OK:

@@ -101,6 +101,7 @@ struct vx_ctx {
   uint32_t max_slots = 0;   // frames per batch (one visibility launch)
   uint32_t table_sets = 0;  // frames per fill -> vote -> emit launch
   uint32_t log2_target = 18, log2_input = 15;
+  int vis_mode = 0;  // 0 by batch size, 1 throughput shape, 2 latency shape (vx_options.vis_mode)
   bool keep_tables = false;
   bool tables_dirty = false;  // tables hold the previous batch (debug mode)
   uint32_t dirty_slots = 0;
@@ -488,7 +489,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   // group is filled, is slower -- every launch places its CTAs on the SMs in the same order, so 8 launches of 114
   // CTAs load 114 SMs with 7 CTAs and leave 34 idle; with groups of 148 it still lost 6 % to the single launch.)
   VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS_BEGIN], st));
-  VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, c->d_scratch, n_scratch, c->d_locks, st));
+  VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, c->d_scratch, n_scratch, c->d_locks, c->vis_mode, st));
   VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS], st));
   VX_CUDA(c, vx_launch_pack(c->d_slots, nb, c->nvox, st));
   VX_CUDA(c, cudaEventRecord(c->ev[EV_PACK], st));
@@ -766,6 +767,7 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   if (options) {
     if (options->table_log2_capacity) c->log2_target = options->table_log2_capacity;
     c->keep_tables = (options->debug & 1u) != 0;
+    c->vis_mode = options->vis_mode <= 2u ? (int)options->vis_mode : 0;
   }
   if (c->log2_target < 10) c->log2_target = 10;
   if (c->log2_target > 30) c->log2_target = 30;

@@ -37,38 +37,55 @@
 // bitmap of 4x4x1-voxel blocks (5 % of the steps need the exact bit from global memory); leaving the
 // grid is one zero-field test on the packed position (trace_warp).  Global traffic: one memo read per live visit,
 // one fire-and-forget RED per ray step, one hit-bit gather per live visit.
+#include <type_traits>
+
 #include "vx_launch.h"
 
 namespace {
 
-constexpr int kVisThreads = 128;
-constexpr int kVisWarps = kVisThreads / 32;
-constexpr int kMaxLive = 1280;    // live cells per wave
+// Shape of one frame's CTA.  Two instantiations (bottom of the file):
+//   * THROUGHPUT: 128 threads, waves of <= 1280 live cells, 7 CTAs per SM -- a batch of >= ~1000 frames fills the device with
+//     frames in flight;
+//   * LATENCY: 512 threads, waves of <= 8192 live cells (a whole face of a 256 x 256 x 32 grid), one CTA per SM -- for batches
+//     that cannot fill the device (a GUI rebuild, the 512 x 512 x 64 stress grid, 1001-scan windows): a frame is a chain of
+//     waves, each a few block-wide phases, so fewer and larger waves on more threads cut the time of ONE frame ~3x.
+template <int THREADS, int MAXLIVE, int MAXCHUNKS, int CTAS_PER_SM>
+struct VisCfg {
+  static constexpr int kThreads = THREADS;
+  static constexpr int kWarps = THREADS / 32;
+  static constexpr int kMaxLive = MAXLIVE;      // live cells per wave
+  static constexpr int kMaxChunks = MAXCHUNKS;  // chunk = <= 32 consecutive z of one column
+  static constexpr int kChunksPerThread = (MAXCHUNKS + THREADS - 1) / THREADS;
+  static constexpr int kLivePerThread = (MAXLIVE + THREADS - 1) / THREADS;
+  static constexpr int kCtasPerSm = CTAS_PER_SM;
+  // casters per tracing warp when a wave's rays are dealt out: a full warp where frames in flight fill the device (most lanes
+  // per instruction), half a warp where one frame has an SM to itself (more warps, shorter critical path)
+  static constexpr uint32_t kRaysPerTracer = THREADS >= 256 ? 16u : 32u;
+  static_assert(THREADS % 32 == 0 && MAXLIVE % 32 == 0 && MAXLIVE / 32 <= THREADS, "bitsets are cleared by one thread per word");
+  static_assert(MAXLIVE < 32768 && MAXCHUNKS <= 2048, "live ranks and chunk << 5 | bit are kept in 16 bits (bit 15 is a flag)");
+};
 constexpr int kAxisTable = 560;   // nx + ny + nz entries of the per-pass ray set-up table (256 + 256 + 32 = 544)
-constexpr int kMaxChunks = 256;   // chunk = <= 32 consecutive z of one column
-constexpr int kChunksPerThread = kMaxChunks / kVisThreads;
-constexpr int kLivePerThread = kMaxLive / kVisThreads;
 constexpr uint32_t kSet = 0x80000000u;
 constexpr uint32_t kEpochShift = 25;
 constexpr uint32_t kIdMask = (1u << kEpochShift) - 1u;
 constexpr uint32_t kMaxEpoch = 127;       // epochs 1..127 (0 = never written)
 constexpr uint32_t kCoarseWords = 4096;   // 131072 block bits
 constexpr uint32_t kRefillLanes = 8;      // idle lanes that trigger a refill of the tracer warp
-constexpr uint32_t kRaysPerTracer = 32;   // casters per tracing warp (more warps = shorter critical path)
 
+template <class C>
 struct VisShared {
   uint32_t coarse[kCoarseWords];    // bit per (2^s x 2^s x 1) block: any voxel occupied
-  uint32_t owner[kMaxLive];         // per live cell: 0 unset | kSet + ray id; cnt[] of candidates during B
-  uint16_t rcell[kMaxLive];         // live rank -> chunk << 5 | bit
-  uint16_t cand[kMaxLive];          // live ranks of the candidates, then of the casters, in visit order
-  uint32_t chmask[kMaxChunks];      // live mask of a chunk
-  uint16_t chbase[kMaxChunks];      // live rank of its first live cell
-  uint32_t killed[kMaxLive / 32];   // per live rank: crossed by a decided caster
-  uint32_t decided[kMaxLive / 32];  // per candidate slot
-  uint32_t castbit[kMaxLive / 32];  // per candidate slot
-  uint32_t has_succ[kMaxLive / 32]; // per candidate slot: its in-face ray crosses a later candidate
+  uint32_t owner[C::kMaxLive];         // per live cell: 0 unset | kSet + ray id; cnt[] of candidates during B
+  uint16_t rcell[C::kMaxLive];         // live rank -> chunk << 5 | bit
+  uint16_t cand[C::kMaxLive];          // live ranks of the candidates, then of the casters, in visit order
+  uint32_t chmask[C::kMaxChunks];      // live mask of a chunk
+  uint16_t chbase[C::kMaxChunks];      // live rank of its first live cell
+  uint32_t killed[C::kMaxLive / 32];   // per live rank: crossed by a decided caster
+  uint32_t decided[C::kMaxLive / 32];  // per candidate slot
+  uint32_t castbit[C::kMaxLive / 32];  // per candidate slot
+  uint32_t has_succ[C::kMaxLive / 32]; // per candidate slot: its in-face ray crosses a later candidate
   float axis[kAxisTable];           // per pass: +-DeltaT of a ray starting at x = i | y = j | z = k (sign = Step)
-  uint32_t warp_sums[kVisWarps];
+  uint32_t warp_sums[C::kWarps];
   uint32_t scan_total;
   uint32_t ncols_ok;
   uint32_t any_edge;
@@ -92,8 +109,10 @@ struct Stats {
 struct Frame {
   VxGridGeom g;
   int32_t cpc;       // chunks per column = ceil(nz / 32)
-  int32_t cshift;    // coarse block = (1 << cshift)^2 x 1 voxels; -1: no coarse bitmap (grid too large)
-  int32_t cyb;       // coarse blocks along y
+  // coarse occupancy: bit k & 31 of word (bi << csI | bj << csJ | k >> 5), bi = i >> cshift, bj = j >> cshift: all strides are
+  // powers of two, so a ray step finds its word with shifts and masks only.  A grid too large for the bitmap gets
+  // cshift = 11 (one block) with every bit set: "look at the exact bit" everywhere.
+  uint32_t cshift, csI, csJ, cmask;
   const uint32_t* __restrict__ occ;
   uint32_t* live;    // [words] free and (invalid pass) not killed
   uint32_t* memo;    // [nvox] epoch << 25 | id of the latest ray of that pass
@@ -121,7 +140,8 @@ __device__ __forceinline__ uint32_t extract_bits(const uint32_t* bits, uint32_t 
 }
 
 // exclusive prefix sum of one value per thread over the CTA; total in sm.scan_total (valid after return)
-__device__ __forceinline__ uint32_t block_scan(VisShared& sm, uint32_t v) {
+template <class C>
+__device__ __forceinline__ uint32_t block_scan(VisShared<C>& sm, uint32_t v) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint32_t x = v;
 #pragma unroll
@@ -134,7 +154,7 @@ __device__ __forceinline__ uint32_t block_scan(VisShared& sm, uint32_t v) {
   __syncthreads();
   uint32_t before = 0, total = 0;
 #pragma unroll
-  for (int w = 0; w < kVisWarps; ++w) {
+  for (int w = 0; w < C::kWarps; ++w) {
     const uint32_t s = sm.warp_sums[w];
     if ((uint32_t)w < warp) before += s;
     total += s;
@@ -165,7 +185,8 @@ __device__ __forceinline__ void wave_cell(const Frame& f, const Wave& w, uint32_
 }
 
 // live rank of (i,j,k) inside the wave, or -1
-__device__ __forceinline__ int32_t live_rank(const Frame& f, const Wave& w, const VisShared& sm, int32_t i, int32_t j, int32_t k) {
+template <class C>
+__device__ __forceinline__ int32_t live_rank(const Frame& f, const Wave& w, const VisShared<C>& sm, int32_t i, int32_t j, int32_t k) {
   const int32_t fx = w.face == 0 ? i : j;
   const int32_t col = (w.face == 0 ? j : i) - w.a_begin;
   if (fx != w.fixed || (uint32_t)col >= (uint32_t)w.ncols) return -1;
@@ -176,10 +197,13 @@ __device__ __forceinline__ int32_t live_rank(const Frame& f, const Wave& w, cons
   return (int32_t)((uint32_t)sm.chbase[c] + (uint32_t)__popc(m & ((1u << bit) - 1u)));
 }
 
-__device__ __forceinline__ bool coarse_set(const Frame& f, const VisShared& sm, int32_t i, int32_t j, int32_t k) {
-  if (f.cshift < 0) return true;
-  const uint32_t C = ((uint32_t)(i >> f.cshift) * (uint32_t)f.cyb + (uint32_t)(j >> f.cshift)) * (uint32_t)f.g.nz + (uint32_t)k;
-  return (sm.coarse[C >> 5] >> (C & 31u)) & 1u;
+__device__ __forceinline__ uint32_t coarse_word(const Frame& f, uint32_t i, uint32_t j, uint32_t k) {
+  return ((i >> f.cshift) << f.csI) | ((j >> f.cshift) << f.csJ) | (k >> 5);
+}
+
+template <class C>
+__device__ __forceinline__ bool coarse_set(const Frame& f, const VisShared<C>& sm, int32_t i, int32_t j, int32_t k) {
+  return (sm.coarse[coarse_word(f, (uint32_t)i, (uint32_t)j, (uint32_t)k)] >> ((uint32_t)k & 31u)) & 1u;
 }
 
 __device__ __forceinline__ bool occupied_exact(const Frame& f, int32_t i, int32_t j, int32_t k) {
@@ -187,14 +211,16 @@ __device__ __forceinline__ bool occupied_exact(const Frame& f, int32_t i, int32_
   return (__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u;
 }
 
-__device__ __forceinline__ bool occupied(const Frame& f, const VisShared& sm, int32_t i, int32_t j, int32_t k) {
+template <class C>
+__device__ __forceinline__ bool occupied(const Frame& f, const VisShared<C>& sm, int32_t i, int32_t j, int32_t k) {
   return coarse_set(f, sm, i, j, k) && occupied_exact(f, i, j, k);
 }
 
 // Ray set-up (VoxelGrid.cpp:249-270).  DeltaT, Step and NextCrossingT of an axis depend only on that axis'
 // start coordinate and the pass's endpoint, so a pass tabulates them once (nx + ny + nz divisions) and a ray
 // starts with three shared-memory loads instead of three IEEE divisions.
-__device__ __forceinline__ void ray_begin(const Frame& f, const VisShared& sm, VxRay& r, int32_t i, int32_t j, int32_t k) {
+template <class C>
+__device__ __forceinline__ void ray_begin(const Frame& f, const VisShared<C>& sm, VxRay& r, int32_t i, int32_t j, int32_t k) {
   if (!f.tables) {
     r.begin(f.g, i, j, k, f.e0, f.e1, f.e2);
     return;
@@ -222,12 +248,13 @@ __device__ __forceinline__ void ray_begin(const Frame& f, const VisShared& sm, V
 
 // Tabulates the pass (all threads).  Leaves f.tables false when the grid is too large for the table or when
 // an entry would need the reference's special cases (subnormal DeltaT, a -0.0 direction).
-__device__ void build_axis_table(Frame& f, VisShared& sm) {
+template <class C>
+__device__ void build_axis_table(Frame& f, VisShared<C>& sm) {
   const int32_t total = f.g.nx + f.g.ny + f.g.nz;
   f.tables = false;
   if (total > kAxisTable) return;
   bool bad = false;
-  for (int32_t x = (int32_t)threadIdx.x; x < total; x += kVisThreads) {
+  for (int32_t x = (int32_t)threadIdx.x; x < total; x += C::kThreads) {
     const int32_t axis = x < f.g.nx ? 0 : (x < f.g.nx + f.g.ny ? 1 : 2);
     const int32_t c = axis == 0 ? x : (axis == 1 ? x - f.g.nx : x - f.g.nx - f.g.ny);
     const float e = axis == 0 ? f.e0 : (axis == 1 ? f.e1 : f.e2);
@@ -242,7 +269,8 @@ __device__ void build_axis_table(Frame& f, VisShared& sm) {
 }
 
 // The first step of the ray from (i,j,k) is along `normal`: its in-face part is empty.
-__device__ __forceinline__ bool normal_first(const Frame& f, const VisShared& sm, int32_t i, int32_t j, int32_t k, int32_t normal) {
+template <class C>
+__device__ __forceinline__ bool normal_first(const Frame& f, const VisShared<C>& sm, int32_t i, int32_t j, int32_t k, int32_t normal) {
   if (f.tables) {
     const float tx = VX_FMUL(0.5f, fabsf(sm.axis[i])), ty = VX_FMUL(0.5f, fabsf(sm.axis[f.g.nx + j]));
     const float tz = VX_FMUL(0.5f, fabsf(sm.axis[f.g.nx + f.g.ny + k]));
@@ -260,8 +288,8 @@ __device__ __forceinline__ bool normal_first(const Frame& f, const VisShared& sm
 
 // In-face part of candidate rc's ray: fn(x) for every live wave cell x visited after rc that it crosses
 // before it leaves the face, hits an occupied cell or terminates.
-template <class Fn>
-__device__ __forceinline__ void prefix_walk(const Frame& f, const Wave& w, const VisShared& sm, uint32_t rc, Fn fn) {
+template <class C, class Fn>
+__device__ __forceinline__ void prefix_walk(const Frame& f, const Wave& w, const VisShared<C>& sm, uint32_t rc, Fn fn) {
   int32_t i, j, k;
   wave_cell(f, w, sm.rcell[rc], i, j, k);
   VxRay r;
@@ -286,15 +314,8 @@ __device__ __forceinline__ void prefix_walk(const Frame& f, const Wave& w, const
 // that reaches the size.
 constexpr uint32_t kPosJ = 11, kPosK = 22, kPosMaskIJ = 0x7FFu;
 
-__device__ __forceinline__ bool coarse_set_packed(const Frame& f, const VisShared& sm, uint32_t P) {
-  if (f.cshift < 0) return true;
-  const uint32_t m = kPosMaskIJ >> f.cshift;
-  const uint32_t bi = (P >> f.cshift) & m, bj = (P >> (kPosJ + f.cshift)) & m, k = P >> kPosK;
-  const uint32_t C = (bi * (uint32_t)f.cyb + bj) * (uint32_t)f.g.nz + k;
-  return (sm.coarse[C >> 5] >> (C & 31u)) & 1u;
-}
-
-__device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_t n_cast, uint32_t id_base, Stats& st) {
+template <class C>
+__device__ void trace_warp(const Frame& f, const Wave& w, VisShared<C>& sm, uint32_t n_cast, uint32_t id_base, uint32_t first_grab, Stats& st) {
   const uint32_t lane = threadIdx.x & 31u;
   const int32_t normal = w.face == 0 ? 0 : 1;
   const uint32_t enc_epoch = f.epoch << kEpochShift;
@@ -304,25 +325,88 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
   // the wrapped -1 when the ray starts on layer 0 (it can only step out).  No coordinate of a ray that is still inside
   // equals its OUT value, so "some field of P ^ OUT is zero" is exactly "the step left the grid".
   constexpr uint32_t kFieldLow = 1u | (1u << kPosJ) | (1u << kPosK), kFieldHigh = (1u << (kPosJ - 1)) | (1u << (kPosK - 1)) | (1u << 31);
-  uint32_t pend = f.pend;
-  asm volatile("" : "+r"(pend));  // opaque: otherwise the compiler rebuilds it from ex / ey / ez in every iteration of the loop
-  bool active = false, exhausted = false, in_face = false, refill = true;
-  uint32_t rc = 0, id = 0, len = 0, L = 0, P = 0, OUT = 0;
+  constexpr uint32_t kFull = 0xFFFFFFFFu;
+  // warp-uniform constants of the coarse lookup (kept opaque: otherwise they are re-derived from `f` inside the loop)
+  uint32_t pend = f.pend, cs_i = f.cshift, cs_j = kPosJ + f.cshift, cmask = f.cmask, csI = f.csI, csJ = f.csJ;
+  asm volatile("" : "+r"(pend), "+r"(cs_i), "+r"(cs_j), "+r"(cmask), "+r"(csI), "+r"(csJ));
+  const uint32_t* __restrict__ coarse = sm.coarse;
+
+  // One lane = one ray.  A lane without a ray is FROZEN (all increments zero, parked on its last cell) and masked out of
+  // every side effect by `act`, so that the step below needs no branch for it.
+  uint32_t act = 0u, fin = 0u, cbit = 0u;  // fin / cbit, of the step just made: the ray ended without a hit | its new cell may be occupied
+  bool exhausted = false, in_face = false, refill = true;
+  uint32_t rc = 0, tag = 0, len = 0, L = 0, P = 0, OUT = 0;
   int32_t dPx = 0, dPy = 0, dPz = 0, dLx = 0, dLy = 0, dLz = 0;
   float tx = 0.f, ty = 0.f, tz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+
+  // One step of VoxelGrid::occludedBy for every lane: which axis (VoxelGrid.cpp:299-301,
+  // {2,1,2,1,2,2,0,0}[(tx<ty)<<2 | (tx<tz)<<1 | (ty<tz)]: axis 0 iff tx<ty && tx<tz, axis 1 iff !(tx<ty) && ty<tz, else 2), the step
+  // itself (:304-305), the memo mark of the cell that is left, the two ways of ending without a hit (:307-308) and the
+  // coarse occupancy bit of the cell that is entered.  This is the unit of work of the whole path, and a warp's lanes take
+  // different axes all the time: it is written as predicated PTX (the compiler turns the C++ form into branches, which
+  // serialise the three axes), ~35 instructions without a branch.  FACE: rays that are still inside the wave's face tell
+  // the cells they cross (visited at or after the caster) that this ray is their latest.
+  auto step = [&](auto face) {
+    if (decltype(face)::value && in_face) {
+      const bool lt01 = tx < ty, lt02 = tx < tz, lt12 = ty < tz;
+      const bool a0 = lt01 && lt02;
+      const bool a1 = !lt01 && lt12;
+      const int32_t x = live_rank(f, w, sm, (int32_t)(P & kPosMaskIJ), (int32_t)((P >> kPosJ) & kPosMaskIJ), (int32_t)(P >> kPosK));
+      if (x >= (int32_t)rc) atomicMax(&sm.owner[x], kSet | (tag & kIdMask));
+      in_face = !(normal == 0 ? a0 : a1);
+    }
+    uint32_t* const mark = f.memo + L;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred a0, a1, a01, on;\n\t"
+        "setp.lt.f32 a0, %0, %1;\n\t"
+        "setp.lt.and.f32 a0, %0, %2, a0;\n\t"
+        "setp.lt.f32 a1, %1, %2;\n\t"
+        "setp.geu.and.f32 a1, %0, %1, a1;\n\t"
+        "or.pred a01, a0, a1;\n\t"
+        "setp.ne.u32 on, %16, 0;\n\t"
+        "@on red.relaxed.gpu.global.max.u32 [%14], %15;\n\t"
+        "@a0 add.rn.f32 %0, %0, %5;\n\t"
+        "@a1 add.rn.f32 %1, %1, %6;\n\t"
+        "@!a01 add.rn.f32 %2, %2, %7;\n\t"
+        "@a0 add.u32 %3, %3, %8;\n\t"
+        "@a1 add.u32 %3, %3, %9;\n\t"
+        "@!a01 add.u32 %3, %3, %10;\n\t"
+        "@a0 add.u32 %4, %4, %11;\n\t"
+        "@a1 add.u32 %4, %4, %12;\n\t"
+        "@!a01 add.u32 %4, %4, %13;\n\t"
+        "}"
+        : "+f"(tx), "+f"(ty), "+f"(tz), "+r"(P), "+r"(L)
+        : "f"(dx), "f"(dy), "f"(dz), "r"(dPx), "r"(dPy), "r"(dPz), "r"(dLx), "r"(dLy), "r"(dLz), "l"(mark), "r"(tag), "r"(act)
+        : "memory");
+    len += act;
+    // leaves the grid (pos == Out after a positive step; 0 or wrapped after a negative one: Out = 0 there, and a step to -1
+    // ends at the top of the reference loop), or reaches the end voxel: the ray misses
+    const uint32_t diff = P ^ OUT;
+    fin = ((((diff - kFieldLow) & ~diff & kFieldHigh) != 0u) || (P == pend)) ? 1u : 0u;
+    // (a step that left the grid has a wrapped or oversized field in P: the index is masked into the bitmap and the bit it reads
+    // is ignored, `fin` decides)
+    const uint32_t cw = ((((P >> cs_i) & cmask) << csI) | (((P >> cs_j) & cmask) << csJ) | (P >> (kPosK + 5))) & (kCoarseWords - 1u);
+    cbit = (coarse[cw] >> ((P >> kPosK) & 31u)) & 1u;
+  };
+
   for (;;) {
-    if (refill) {  // warp-uniform: some lane ended its ray in the previous iteration (or this is the first one)
-      const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
-      if (!exhausted && (idle == 0xFFFFFFFFu || (uint32_t)__popc(idle) >= kRefillLanes)) {
+    if (refill) {  // warp-uniform: some lane ended its ray (or this is the first round)
+      const uint32_t idle = __ballot_sync(kFull, act == 0u);
+      if (!exhausted && (idle == kFull || (uint32_t)__popc(idle) >= kRefillLanes)) {
+        // the first grab of a warp is its share of the wave's casters (all tracing warps start with rays), later ones fill every idle lane
+        const uint32_t take = min((uint32_t)__popc(idle), first_grab);
+        first_grab = 32u;
         uint32_t base = 0;
-        if (lane == (uint32_t)(__ffs(idle) - 1)) base = atomicAdd(&sm.queue, (uint32_t)__popc(idle));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(idle) - 1);
-        if (base + (uint32_t)__popc(idle) >= n_cast) exhausted = true;
-        if (!active) {
-          const uint32_t s = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        if (lane == (uint32_t)(__ffs(idle) - 1)) base = atomicAdd(&sm.queue, take);
+        base = __shfl_sync(kFull, base, __ffs(idle) - 1);
+        if (base + take >= n_cast) exhausted = true;
+        const uint32_t mine = (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        if (act == 0u && mine < take) {
+          const uint32_t s = base + mine;
           if (s < n_cast) {
             rc = sm.cand[s];
-            id = id_base + s;
+            tag = enc_epoch | (id_base + s);
             int32_t i, j, k;
             wave_cell(f, w, sm.rcell[rc], i, j, k);
             VxRay r0;
@@ -340,63 +424,54 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared& sm, uint32_
             OUT = (r0.sx > 0 ? (uint32_t)f.g.nx : (i == 0 ? kPosMaskIJ : 0u)) | ((r0.sy > 0 ? (uint32_t)f.g.ny : (j == 0 ? kPosMaskIJ : 0u)) << kPosJ) |
                   ((r0.sz > 0 ? (uint32_t)f.g.nz : (k == 0 ? 0x3FFu : 0u)) << kPosK);
             L = lin(f.g, i, j, k);
-            active = true;
+            act = 1u;
             in_face = true;
             len = 0;
             ++st.rays;
           }
         }
       }
-      if (!__any_sync(0xFFFFFFFFu, active)) {
+      if (!__any_sync(kFull, act != 0u)) {
         if (exhausted) break;
         continue;
       }
     }
-    bool finished = false;
-    if (active) {
-      // P = the current cell: inside the grid and free.  Which axis steps next (VoxelGrid.cpp:299-301):
-      // {2,1,2,1,2,2,0,0}[(tx<ty)<<2 | (tx<tz)<<1 | (ty<tz)].  Select-based: a warp running alone pays for
-      // every branch, and this loop is the critical path of a wave.
-      const bool lt01 = tx < ty, lt02 = tx < tz, lt12 = ty < tz;
-      const bool a0 = lt01 && lt02;
-      const bool a1 = !lt01 && lt12;
-      const bool a01 = a0 || a1;
-      const uint32_t Lc = L;
-      if (in_face) {  // cells of this wave visited at or after the caster see this ray
-        const int32_t x = live_rank(f, w, sm, (int32_t)(P & kPosMaskIJ), (int32_t)((P >> kPosJ) & kPosMaskIJ), (int32_t)(P >> kPosK));
-        if (x >= (int32_t)rc) atomicMax(&sm.owner[x], kSet | id);
-        in_face = !(normal == 0 ? a0 : a1);
-      }
-      // step (VoxelGrid.cpp:304-305)
-      const float ntx = VX_FADD(tx, dx), nty = VX_FADD(ty, dy), ntz = VX_FADD(tz, dz);
-      tx = a0 ? ntx : tx;
-      ty = a1 ? nty : ty;
-      tz = a01 ? tz : ntz;
-      P += (uint32_t)(a0 ? dPx : (a1 ? dPy : dPz));
-      L += (uint32_t)(a0 ? dLx : (a1 ? dLy : dLz));
-      // leaves the grid (pos == Out after a positive step; 0 or wrapped after a negative one: Out = 0 there, and
-      // a step to -1 ends at the top of the reference loop), or reaches the end voxel: the ray misses
-      const uint32_t diff = P ^ OUT;
-      finished = (((diff - kFieldLow) & ~diff & kFieldHigh) != 0u) | (P == pend);
-      vx_red_max(&f.memo[Lc], enc_epoch | id);
-      ++len;
+    // ---- step until some lane needs attention (its ray ended, or the exact occupancy bit has to decide)
+    uint32_t attn;
+    if (__any_sync(kFull, in_face)) {
+      do {
+        step(std::true_type{});
+        attn = act & (fin | cbit);
+      } while (!__any_sync(kFull, attn != 0u) && __any_sync(kFull, in_face));
+    } else {
+      do {
+        step(std::false_type{});
+        attn = act & (fin | cbit);
+      } while (!__any_sync(kFull, attn != 0u));
+    }
+    // ---- attention
+    bool done = false;
+    if (attn) {
       bool hit = false;
-      if (!finished && coarse_set_packed(f, sm, P)) {  // ~5 % of the steps: the exact bit decides
-        hit = (__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u;
-        finished = hit;
-      }
-      if (finished) {
-        if (hit) vx_red_or(&f.hitbits[id >> 5], 1u << (id & 31u));
+      if (!fin) hit = (__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u;  // ~5 % of the steps: the exact bit decides
+      if (fin || hit) {
+        if (hit) vx_red_or(&f.hitbits[(tag & kIdMask) >> 5], 1u << (tag & 31u));
         st.steps += len;
-        active = false;
+        done = true;
+        act = 0u;  // freeze the lane
+        in_face = false;
+        dx = dy = dz = 0.f;
+        dPx = dPy = dPz = 0;
+        dLx = dLy = dLz = 0;
       }
     }
-    refill = __any_sync(0xFFFFFFFFu, finished);
+    refill = __any_sync(kFull, done);
   }
 }
 
 // Runs the columns [a, a + range) of one face as far as one wave reaches; returns the columns consumed.
-__device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t a, int32_t range, VisShared& sm, uint32_t& id_base,
+template <class C>
+__device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t a, int32_t range, VisShared<C>& sm, uint32_t& id_base,
                             Stats& st) {
   const uint32_t tid = threadIdx.x;
   long long t0 = clock64();
@@ -407,11 +482,11 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
 
   // ---- A1: live masks of the chunks of the range, ranks by prefix sum
   const uint32_t n_chunks = (uint32_t)range * (uint32_t)f.cpc;
-  uint32_t masks[kChunksPerThread];
+  uint32_t masks[C::kChunksPerThread];
   uint32_t local = 0;
 #pragma unroll
-  for (int u = 0; u < kChunksPerThread; ++u) {
-    const uint32_t c = tid * kChunksPerThread + (uint32_t)u;
+  for (int u = 0; u < C::kChunksPerThread; ++u) {
+    const uint32_t c = tid * C::kChunksPerThread + (uint32_t)u;
     masks[u] = 0;
     if (c < n_chunks) {
       uint32_t col, part;
@@ -439,21 +514,21 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   {
     uint32_t run = base;
 #pragma unroll
-    for (int u = 0; u < kChunksPerThread; ++u) {
-      const uint32_t c = tid * kChunksPerThread + (uint32_t)u;
+    for (int u = 0; u < C::kChunksPerThread; ++u) {
+      const uint32_t c = tid * C::kChunksPerThread + (uint32_t)u;
       if (c < n_chunks) {
         sm.chmask[c] = masks[u];
         sm.chbase[c] = (uint16_t)(run < 0xFFFFu ? run : 0xFFFFu);
         run += (uint32_t)__popc(masks[u]);
         // last chunk of a column: the column fits if the live cells up to and including it do
-        if ((c + 1u) % (uint32_t)f.cpc == 0u && run <= (uint32_t)kMaxLive) atomicMax(&sm.ncols_ok, c / (uint32_t)f.cpc + 1u);
+        if ((c + 1u) % (uint32_t)f.cpc == 0u && run <= (uint32_t)C::kMaxLive) atomicMax(&sm.ncols_ok, c / (uint32_t)f.cpc + 1u);
       }
     }
   }
   __syncthreads();
   const uint32_t total_live = sm.scan_total;
   if (total_live == 0) return range;  // nothing alive in these columns
-  w.ncols = (int32_t)sm.ncols_ok;     // >= 1: one column holds at most nz <= kMaxLive live cells
+  w.ncols = (int32_t)sm.ncols_ok;     // >= 1: one column holds at most nz <= C::kMaxLive live cells
   const uint32_t wave_chunks = (uint32_t)w.ncols * (uint32_t)f.cpc;
   const uint32_t last = wave_chunks - 1u;
   const uint32_t n_live = (uint32_t)sm.chbase[last] + (uint32_t)__popc(sm.chmask[last]);
@@ -462,8 +537,8 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
 
   // ---- A2: rank -> cell
 #pragma unroll
-  for (int u = 0; u < kChunksPerThread; ++u) {
-    const uint32_t c = tid * kChunksPerThread + (uint32_t)u;
+  for (int u = 0; u < C::kChunksPerThread; ++u) {
+    const uint32_t c = tid * C::kChunksPerThread + (uint32_t)u;
     if (c < wave_chunks) {
       uint32_t m = masks[u];
       uint32_t r = sm.chbase[c];
@@ -477,11 +552,11 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   __syncthreads();
 
   // ---- A3: snapshot of the memo; candidates in visit order
-  const uint32_t per = (n_live + kVisThreads - 1) / kVisThreads;
+  const uint32_t per = (n_live + C::kThreads - 1) / C::kThreads;
   const uint32_t r_begin = min(n_live, tid * per), r_end = min(n_live, r_begin + per);
-  uint32_t m[kLivePerThread];
+  uint32_t m[C::kLivePerThread];
 #pragma unroll
-  for (int u = 0; u < kLivePerThread; ++u) {
+  for (int u = 0; u < C::kLivePerThread; ++u) {
     const uint32_t r = r_begin + (uint32_t)u;
     m[u] = 0;
     if (r < r_end) {
@@ -492,7 +567,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   }
   uint32_t cand_flags = 0;
 #pragma unroll
-  for (int u = 0; u < kLivePerThread; ++u) {
+  for (int u = 0; u < C::kLivePerThread; ++u) {
     const uint32_t r = r_begin + (uint32_t)u;
     if (r < r_end) {
       if ((m[u] >> kEpochShift) == f.epoch) {
@@ -505,9 +580,9 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   }
   uint32_t cslot = block_scan(sm, (uint32_t)__popc(cand_flags));
 #pragma unroll
-  for (int u = 0; u < kLivePerThread; ++u)
+  for (int u = 0; u < C::kLivePerThread; ++u)
     if ((cand_flags >> u) & 1u) sm.cand[cslot++] = (uint16_t)(r_begin + (uint32_t)u);
-  if (tid < kMaxLive / 32) {
+  if (tid < C::kMaxLive / 32) {
     sm.killed[tid] = 0;
     sm.decided[tid] = 0;
     sm.castbit[tid] = 0;
@@ -529,7 +604,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
     // the ray again: up to eight live ranks, 16 bits each.
     unsigned long long crossed = 0, crossed_hi = 0;
     uint32_t n_crossed = 0;  // > 8: more than fit, walk again
-    for (uint32_t p = tid; p < n_cand; p += kVisThreads) {
+    for (uint32_t p = tid; p < n_cand; p += C::kThreads) {
       const uint32_t rc = sm.cand[p];
       int32_t i, j, k;
       wave_cell(f, w, sm.rcell[rc], i, j, k);
@@ -558,7 +633,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       for (;;) {
         st.rounds += 1;
         bool waiting = false;  // one of this thread's candidates is still undecided after the sweep
-        for (uint32_t p = tid; p < n_cand; p += kVisThreads) {
+        for (uint32_t p = tid; p < n_cand; p += C::kThreads) {
           const uint32_t pbit = 1u << (p & 31u);
           if (sm.decided[p >> 5] & pbit) continue;
           const uint32_t rc = sm.cand[p];
@@ -594,12 +669,12 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
         if (!__syncthreads_or(waiting ? 1 : 0)) break;  // (one barrier per sweep: it also carries the verdict)
       }
       // cnt[] back to "unset"; casters compacted in visit order (read everything, then write)
-      const uint32_t cper = (n_cand + kVisThreads - 1) / kVisThreads;
+      const uint32_t cper = (n_cand + C::kThreads - 1) / C::kThreads;
       const uint32_t p_begin = min(n_cand, tid * cper), p_end = min(n_cand, p_begin + cper);
-      uint16_t keep[kLivePerThread];
+      uint16_t keep[C::kLivePerThread];
       uint32_t nkeep = 0;
 #pragma unroll
-      for (int u = 0; u < kLivePerThread; ++u) {
+      for (int u = 0; u < C::kLivePerThread; ++u) {
         const uint32_t p = p_begin + (uint32_t)u;
         keep[u] = 0;
         if (p < p_end) {
@@ -613,7 +688,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       }
       uint32_t dst = block_scan(sm, nkeep);  // its barriers separate the reads above from the writes below
 #pragma unroll
-      for (int u = 0; u < kLivePerThread; ++u)
+      for (int u = 0; u < C::kLivePerThread; ++u)
         if (keep[u] & 0x8000u) sm.cand[dst++] = (uint16_t)(keep[u] & 0x7FFFu);
       __syncthreads();
       n_cast = sm.scan_total;
@@ -627,9 +702,9 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
     }
 
     // ---- C: trace
-    uint32_t tracers = (n_cast + kRaysPerTracer - 1u) / kRaysPerTracer;
-    if (tracers > (uint32_t)kVisWarps) tracers = kVisWarps;
-    if ((tid >> 5) < tracers) trace_warp(f, w, sm, n_cast, id_base, st);
+    uint32_t tracers = (n_cast + C::kRaysPerTracer - 1u) / C::kRaysPerTracer;
+    if (tracers > (uint32_t)C::kWarps) tracers = C::kWarps;
+    if ((tid >> 5) < tracers) trace_warp(f, w, sm, n_cast, id_base, min(32u, (n_cast + tracers - 1u) / tracers), st);
     __syncthreads();
     {
       const long long t1 = clock64();
@@ -641,10 +716,10 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   // ---- D: apply the visit.  All hit-bit gathers of a thread are in flight together (they were one
   // dependent L2 / DRAM round trip per cell before).
   {
-    uint32_t own[kLivePerThread], hw[kLivePerThread];
+    uint32_t own[C::kLivePerThread], hw[C::kLivePerThread];
 #pragma unroll
-    for (int u = 0; u < kLivePerThread; ++u) {
-      const uint32_t r = tid + (uint32_t)u * kVisThreads;
+    for (int u = 0; u < C::kLivePerThread; ++u) {
+      const uint32_t r = tid + (uint32_t)u * C::kThreads;
       own[u] = 0;
       hw[u] = 0;
       if (r < n_live) {
@@ -653,8 +728,8 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       }
     }
 #pragma unroll
-    for (int u = 0; u < kLivePerThread; ++u) {
-      const uint32_t r = tid + (uint32_t)u * kVisThreads;
+    for (int u = 0; u < C::kLivePerThread; ++u) {
+      const uint32_t r = tid + (uint32_t)u * C::kThreads;
       if (r >= n_live) break;
       const bool hit = (own[u] & kSet) && ((hw[u] >> (own[u] & 31u)) & 1u);
       if (f.inv && hit) continue;  // the common case: still occluded from this endpoint, nothing to do
@@ -675,14 +750,13 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   return w.ncols;
 }
 
-constexpr int kVisCtasPerSm = 7;  // 7 x (30 KB + 1 KB) of shared memory, 7 x 128 x 72 registers
-
-__global__ void __launch_bounds__(kVisThreads, kVisCtasPerSm)
+template <class C>
+__global__ void __launch_bounds__(C::kThreads, C::kCtasPerSm)
 vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restrict__ frames,
                      const float* __restrict__ endpoints, const VxGridGeom g, const uint32_t hit_words,
                      const VxVisScratch* __restrict__ scratch, const uint32_t n_scratch, uint32_t* locks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  VisShared& sm = *reinterpret_cast<VisShared*>(smem_raw);
+  VisShared<C>& sm = *reinterpret_cast<VisShared<C>*>(smem_raw);
   const VxSlot& slot = slots[blockIdx.x];
   const VxVisFrame vf = frames[blockIdx.x];
   const uint32_t tid = threadIdx.x;
@@ -709,29 +783,40 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
   f.memo = scratch[scratch_id].memo;
   f.hitbits = scratch[scratch_id].hitbits;
   f.occl = slot.occl;
-  f.cshift = -1;
-  f.cyb = 0;
-  for (int32_t s = 0; s < 8; ++s) {
-    const uint64_t cxb = (uint64_t)((g.nx + (1 << s) - 1) >> s), cyb = (uint64_t)((g.ny + (1 << s) - 1) >> s);
-    if (cxb * cyb * (uint64_t)g.nz <= (uint64_t)kCoarseWords * 32u) {
+  // coarse bitmap geometry: the smallest block size whose power-of-two padded bitmap fits
+  const uint32_t kw = (uint32_t)((g.nz + 31) >> 5);
+  uint32_t lkw = 0;
+  while ((1u << lkw) < kw) ++lkw;
+  f.cshift = kPosJ;  // fallback: a single block
+  f.cmask = 0u;
+  f.csI = lkw;
+  f.csJ = lkw;
+  bool coarse_ok = false;
+  for (uint32_t s = 0; s < 8u; ++s) {
+    const uint32_t cxb = (uint32_t)((g.nx + (1 << s) - 1) >> s), cyb = (uint32_t)((g.ny + (1 << s) - 1) >> s);
+    uint32_t lcy = 0;
+    while ((1u << lcy) < cyb) ++lcy;
+    if (((uint64_t)cxb << (lcy + lkw)) <= (uint64_t)kCoarseWords) {
       f.cshift = s;
-      f.cyb = (int32_t)cyb;
+      f.cmask = kPosMaskIJ >> s;
+      f.csJ = lkw;
+      f.csI = lcy + lkw;
+      coarse_ok = true;
       break;
     }
   }
-
   // coarse occupancy; live = free cells; occluded starts as "occupied"; no ray has a hit bit yet
-  for (uint32_t x = tid; x < kCoarseWords; x += kVisThreads) sm.coarse[x] = 0;
+  for (uint32_t x = tid; x < kCoarseWords; x += C::kThreads) sm.coarse[x] = coarse_ok ? 0u : 0xFFFFFFFFu;
   __syncthreads();
-  for (uint32_t x = tid; x < words; x += kVisThreads) {
+  for (uint32_t x = tid; x < words; x += C::kThreads) {
     const uint32_t o = __ldg(f.occ + x);
     const uint32_t valid = (x == words - 1u && (nvox & 31u)) ? ((1u << (nvox & 31u)) - 1u) : 0xFFFFFFFFu;
     f.live[x] = ~o & valid;
     f.occl[x] = o;
-    if (o && f.cshift >= 0) {
+    if (o && coarse_ok) {
       if (g.nz == 32) {  // one word = one column
         const uint32_t i = x / (uint32_t)g.ny, j = x - i * (uint32_t)g.ny;
-        atomicOr(&sm.coarse[(i >> f.cshift) * (uint32_t)f.cyb + (j >> f.cshift)], o);
+        atomicOr(&sm.coarse[coarse_word(f, i, j, 0u)], o);
       } else {
         uint32_t bits = o;
         while (bits) {
@@ -740,17 +825,16 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
           const uint32_t L = x * 32u + b;
           const uint32_t k = L % (uint32_t)g.nz, ij = L / (uint32_t)g.nz;
           const uint32_t i = ij / (uint32_t)g.ny, j = ij - i * (uint32_t)g.ny;
-          const uint32_t C = ((i >> f.cshift) * (uint32_t)f.cyb + (j >> f.cshift)) * (uint32_t)g.nz + k;
-          atomicOr(&sm.coarse[C >> 5], 1u << (C & 31u));
+          atomicOr(&sm.coarse[coarse_word(f, i, j, k)], 1u << (k & 31u));
         }
       }
     }
   }
-  for (uint32_t x = tid; x < hit_words; x += kVisThreads) f.hitbits[x] = 0;
+  for (uint32_t x = tid; x < hit_words; x += C::kThreads) f.hitbits[x] = 0;
 
   Stats st;
   const int32_t shells = vx_num_shells(g.nx, g.ny);
-  const int32_t max_cols = kMaxChunks / f.cpc;
+  const int32_t max_cols = C::kMaxChunks / f.cpc;
 
   const uint32_t n_pass = 1u + vf.n_endpoints;
   for (uint32_t pass = 0; pass < n_pass; ++pass) {
@@ -772,7 +856,7 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     f.epoch = (pass % kMaxEpoch) + 1u;
     build_axis_table(f, sm);  // (barrier inside)
     if (pass % kMaxEpoch == 0) {  // first pass, or the epoch counter restarts: forget every memo
-      for (uint32_t x = tid; x < nvox; x += kVisThreads) f.memo[x] = 0u;
+      for (uint32_t x = tid; x < nvox; x += C::kThreads) f.memo[x] = 0u;
     }
     __syncthreads();
 
@@ -789,10 +873,10 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     }
     // the ray ids start again at 0: clear the hit bits this pass used
     const uint32_t used_words = min(hit_words, (id_base + 31u) >> 5);
-    for (uint32_t x = tid; x < used_words; x += kVisThreads) f.hitbits[x] = 0;
+    for (uint32_t x = tid; x < used_words; x += C::kThreads) f.hitbits[x] = 0;
     if (pass == 0) {  // invalid_ = occlusions_ (VoxelGrid.cpp:169): what is not occluded is dead from here on
       uint32_t n_live0 = 0, n_occ = 0;
-      for (uint32_t x = tid; x < words; x += kVisThreads) {
+      for (uint32_t x = tid; x < words; x += C::kThreads) {
         const uint32_t o = __ldg(f.occ + x);
         const uint32_t l = __ldcg(f.occl + x) & ~o;
         f.live[x] = l;
@@ -871,24 +955,45 @@ cudaError_t vx_launch_trace_ray(const uint32_t* occ, VxGridGeom geom, int32_t i,
   return cudaGetLastError();
 }
 
+// 7 x (30 KB + 1 KB) of shared memory and 7 x 128 x 72 registers per SM | one CTA of 512 threads (92 KB) per SM
+using CfgThroughput = VisCfg<128, 1280, 256, 7>;
+using CfgLatency = VisCfg<512, 8192, 1024, 1>;
+
 cudaError_t vx_visibility_prepare() {
-  return cudaFuncSetAttribute(vx_visibility_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisShared));
+  cudaError_t e = cudaFuncSetAttribute(vx_visibility_kernel<CfgThroughput>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(VisShared<CfgThroughput>));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(vx_visibility_kernel<CfgLatency>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisShared<CfgLatency>));
 }
 
+// CTAs of the kernel the device holds at once (the larger of the two shapes: the scratch pool is sized by it)
 int vx_visibility_resident_ctas(int device) {
-  int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vx_visibility_kernel, kVisThreads, sizeof(VisShared)) != cudaSuccess) return 0;
+  int a = 0, b = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, vx_visibility_kernel<CfgThroughput>, CfgThroughput::kThreads,
+                                                    sizeof(VisShared<CfgThroughput>)) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, vx_visibility_kernel<CfgLatency>, CfgLatency::kThreads,
+                                                    sizeof(VisShared<CfgLatency>)) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
-  return per_sm * sms;
+  return (a > b ? a : b) * sms;
 }
 
+// mode: 0 = by batch size (latency shape when the frames cannot even give every SM two CTAs), 1 = throughput, 2 = latency
 cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, uint32_t n_slots,
                                  const float* endpoints, VxGridGeom geom, const VxVisScratch* scratch, uint32_t n_scratch,
-                                 uint32_t* locks, cudaStream_t stream) {
+                                 uint32_t* locks, int mode, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
   const uint32_t hit_words = (uint32_t)(vx_visibility_visits(geom) / 32u + 1u);
-  vx_visibility_kernel<<<n_slots, kVisThreads, sizeof(VisShared), stream>>>(slots, frames, endpoints, geom, hit_words, scratch,
-                                                                           n_scratch, locks);
+  if (mode == 0) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    mode = n_slots <= 2u * (uint32_t)sms ? 2 : 1;
+  }
+  if (mode == 2)
+    vx_visibility_kernel<CfgLatency><<<n_slots, CfgLatency::kThreads, sizeof(VisShared<CfgLatency>), stream>>>(
+        slots, frames, endpoints, geom, hit_words, scratch, n_scratch, locks);
+  else
+    vx_visibility_kernel<CfgThroughput><<<n_slots, CfgThroughput::kThreads, sizeof(VisShared<CfgThroughput>), stream>>>(
+        slots, frames, endpoints, geom, hit_words, scratch, n_scratch, locks);
   return cudaGetLastError();
 }
 
