@@ -650,7 +650,7 @@ def run_extra_configs(vx, torch, args, seq, poses, n_scans, device, ref_line, bu
     cases = [
         ("dense", "semantic_kitti_dense", dict(first=0, frames=600), "configs[2]: stride-1 windows (same per-frame work as configs[1])"),
         ("stress_512", "stress_512", dict(first=0, frames=40), "configs[3]: 512x512x64 @ 0.1 m, 200 scans -> 40 frames"),
-        ("past1000", "past1000", dict(first=0, frames=2), "configs[4]: 1001-scan windows, 1000 updateInvalid passes per frame"),
+        ("past1000", "past1000", dict(first=0, frames=64), "configs[4]: 1001-scan windows, 1000 updateInvalid passes per frame, 64 frames in flight"),
     ]
     for name, cfg_name, sel, what in cases:
         if budget_left() < 60:

@@ -128,7 +128,9 @@ typedef struct vx_stage_times {
   uint64_t dda_steps; /* cells traversed by those rays */
   /* K4 anatomy, summed over frames: waves run, waves that needed the in-wave resolution, resolution
    * sweeps, and SM cycles as seen by thread 0 of each frame's CTA: [0..3] per phase (snapshot, resolve,
-   * trace, apply); [4..7] reserved (zero). */
+   * trace, apply); [4..6] developer statistics of builds with
+   * -DVX_TRACE_STATS (sum over waves of the longest ray in steps, step-loop iterations and attention events of thread 0),
+   * otherwise zero; [7] reserved (zero). */
   uint64_t vis_waves;
   uint64_t vis_resolve_waves;
   uint64_t vis_rounds;

@@ -41,3 +41,5 @@ cyc = np.array(st["vis_cycles"], float)
 print("per frame: rays %.0f steps %.0f waves %.0f resolve %.0f rounds %.0f" % tuple(st[k] / f for k in ("rays_cast", "dda_steps", "vis_waves", "vis_resolve_waves", "vis_rounds")))
 print("cycles per wave  A snapshot %.0f | B resolve %.0f | C trace %.0f | D apply %.0f | total %.0f" % (*(cyc[:4] / st["vis_waves"]), cyc[:4].sum() / st["vis_waves"]))
 print("Gsteps/s", st["dda_steps"] / (st["visibility_ms"] / 1e3) / 1e9)
+if cyc[4] > 0:
+    print("trace anatomy (thread 0): longest ray per wave %.1f steps | loop iterations per wave %.1f | attention events per wave %.1f" % tuple(cyc[4:7] / st["vis_waves"]))

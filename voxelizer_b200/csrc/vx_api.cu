@@ -60,7 +60,7 @@ struct ScratchMem {
 enum { EV_BEGIN = 0, EV_VIS_BEGIN, EV_VIS, EV_PACK, EV_END, EV_COUNT };
 
 // per-slot counter block (uint32 words): used/overflow of both tables, then two 64-bit statistics
-constexpr size_t kCounterWords = 4 + 2 * VX_SLOT_STATS + 2;  // 32 words = 128 bytes per slot
+constexpr size_t kCounterWords = 4 + 2 * VX_SLOT_STATS + 2;  // 38 words per slot
 
 // One asynchronous vx_submit_frames call: the descriptors and every array they point to are copied, so the
 // caller's memory is free again when the call returns (the OUTPUT buffers are the caller's until vx_wait).
@@ -593,6 +593,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   c->times.vis_resolve_waves += stats[3];
   c->times.vis_rounds += stats[4];
   for (int k = 0; k < 4; ++k) c->times.vis_cycles[k] += stats[5 + k];
+  for (int k = 0; k < 3; ++k) c->times.vis_cycles[4 + k] += stats[13 + k];  // developer statistics (VX_TRACE_STATS builds)
   return VX_OK;
 }
 

@@ -14,7 +14,7 @@
 #include "vx_dda.h"
 
 #define VX_MAX_PROBES 4096u
-#define VX_SLOT_STATS 13
+#define VX_SLOT_STATS 16
 
 // Open-addressing histogram of one grid of one frame: (L << 16 | label16) -> count, and the dense
 // per-voxel vote array best[L] = max over labels of (count << 16 | 0xFFFF - label).  Keys are stored + 1
