@@ -712,7 +712,8 @@ def run_strong(vx, torch, dist, args, rank, world, device, host_threads, seq0, r
     rank 0 then runs the whole job alone and the digests are compared."""
     result = {}
     stream = torch.cuda.current_stream().cuda_stream
-    for name, cfg_name, n_scans, max_targets in (("dense", "semantic_kitti_dense", args.scans, None), ("stress_512", "stress_512", 271, 40)):
+    # (the stress job has 240 frames: more than the 148 one GPU runs at a time in the one-CTA-per-SM shape, so that sharding it can pay)
+    for name, cfg_name, n_scans, max_targets in (("dense", "semantic_kitti_dense", args.scans, None), ("stress_512", "stress_512", 1271, 240)):
         cfg = vx.Config(cfg_file(cfg_name))
         params = vx.synth_params(seed=1234)
         poses = vx.synth_velo_poses(params, n_scans).astype(np.float32)
@@ -739,6 +740,7 @@ def run_strong(vx, torch, dist, args, rank, world, device, host_threads, seq0, r
             else:
                 s, own = Sequence(vx, 1234, first, last - first, host_threads), True
             specs, kept, _ = plan_frames(vx, cfg, n_scans, poses, s, targets=tg)
+            warm_up(vx, backend, s, specs, ring, first)
             dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -781,6 +783,21 @@ def run_strong(vx, torch, dist, args, rank, world, device, host_threads, seq0, r
     return result if rank == 0 else None
 
 
+def warm_up(vx, be, seq, specs, ring, first_scan):
+    """Untimed: the first frames of the job once, so that frame records, tables and traversal scratch of this context exist
+    and the kernels are loaded before anything is timed."""
+    part = specs[: min(2, len(specs))]
+    if not part:
+        return
+    last = max(int(max(s.prior_ids.max(), s.past_ids.max() if len(s.past_ids) else 0)) for s in part) + 1
+    seq.upload(be, first_scan, last)
+    outs = output_views(ring, be, len(part))
+    descs, keep = be.build_descs(part, outs)
+    be.wait(be.submit_descs(descs, len(part)))
+    be.sync()
+    be.evict_all()
+
+
 def shard_job_single(vx, be, cfg, n_scans, poses, targets, ring, per_c, seq0, host_threads):
     """The whole job on this rank alone (rank 0, while the others wait at the barrier)."""
     first = max(0, int(targets[0]) - cfg.pod.priorScans)
@@ -790,6 +807,7 @@ def shard_job_single(vx, be, cfg, n_scans, poses, targets, ring, per_c, seq0, ho
     else:
         s, own = Sequence(vx, 1234, first, last - first, host_threads), True
     specs, kept, _ = plan_frames(vx, cfg, n_scans, poses, s, targets=targets)
+    warm_up(vx, be, s, specs, ring, first)
     t0 = time.perf_counter()
     s.upload(be, first, last)
     busy, digests = run_host_job(vx, be, s, specs, ring, max(1, min(len(specs), ring.nbytes // per_c)))

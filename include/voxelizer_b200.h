@@ -76,7 +76,8 @@ typedef struct vx_options {
   uint32_t vis_mode;             /* shape of the traversal kernel: 0 = chosen per batch (few frames: one 512-thread CTA per SM and
                                     whole-face waves, short time per frame; many frames: 7 x 128-thread CTAs per SM, most frames per
                                     second), 1 = always the many-frames shape, 2 = always the few-frames shape.  Same bytes either way. */
-  uint32_t reserved[1];
+  uint32_t occlusion_labels;     /* 1: frames may ask for VoxelGrid::insertOcclusionLabels (VX_FRAME_INSERT_OCCLUSION_LABELS); costs 8 bytes per
+                                    voxel and frame of a batch, and 4 per visit of the traversal's scratch */
 } vx_options;
 
 /* One target frame = one iteration of gen_data.cpp:62-142 that passed the "labelled" gate.
@@ -98,7 +99,17 @@ typedef struct vx_frame_desc {
   uint16_t* out_label;    /* <name>.label     nvox uint16   (target grid majority label)     */
   uint8_t* out_occluded;  /* <name>.occluded  nvox/8 bytes                                   */
   uint8_t* out_invalid;   /* <name>.invalid   nvox/8 bytes                                   */
+  uint32_t flags;         /* vx_frame_flags */
+  uint32_t reserved;
 } vx_frame_desc;
+
+/* VX_FRAME_INSERT_OCCLUSION_LABELS: run VoxelGrid::insertOcclusionLabels (VoxelGrid.cpp:75-96; the calls gen_data.cpp:108-109
+ * and Mainframe.cpp:303-304 have commented out) on the TARGET grid between updateOcclusions and the updateInvalid passes:
+ * every voxel that was empty takes count and labels of the first occupied voxel above it when only occluded empty voxels
+ * lie between; the filled voxels are occupied for the passes that follow.  Needs vx_options.occlusion_labels.
+ * VX_FRAME_INPUT_IS_TARGET: the input grid holds the same points as the target grid (a single VoxelGrid behind the
+ * facade): `.bin` is then packed from the target grid's labels, filled ones included. */
+typedef enum vx_frame_flags { VX_FRAME_INSERT_OCCLUSION_LABELS = 1, VX_FRAME_INPUT_IS_TARGET = 2 } vx_frame_flags;
 
 typedef struct vx_grid_info {
   uint32_t size[3]; /* Sx, Sy, Sz */
@@ -191,7 +202,8 @@ typedef enum vx_dump_kind {
   VX_DUMP_HIST_INPUT = 1,
   VX_DUMP_OCCUPANCY = 2,   /* uint8 per voxel, target grid count > 0               */
   VX_DUMP_OCCLUDED = 3,    /* uint8 per voxel, isOccluded                          */
-  VX_DUMP_INVALID = 4      /* uint8 per voxel, isInvalid                           */
+  VX_DUMP_INVALID = 4,     /* uint8 per voxel, isInvalid                           */
+  VX_DUMP_FILL_SOURCE = 5  /* uint32 per voxel: L of the voxel insertOcclusionLabels copied from, 0xFFFFFFFF if none */
 } vx_dump_kind;
 int vx_debug_dump(vx_ctx* ctx, uint32_t frame_index, int kind, void* dst, uint64_t* count);
 

@@ -195,14 +195,20 @@ int vxt_voxel_grid_probe(int device, float resolution, const float* min3, const 
                          uint32_t n, const float* endpoints3, uint32_t n_endpoints, uint32_t* size3, float* offset3, uint8_t* occluded,
                          uint8_t* is_free, uint8_t* invalid, uint32_t* counts, uint32_t* n_labels, uint32_t* majority, uint32_t n_rays,
                          const int32_t* ray_start, const float* ray_end, int32_t* ray_occluder, int32_t* ray_visited,
-                         uint64_t visited_capacity, uint64_t* ray_offset) {
+                         uint64_t visited_capacity, uint64_t* ray_offset, int insert_occlusion_labels, uint16_t* label_image,
+                         uint8_t* bin_image, uint8_t* occluded_image, uint8_t* invalid_image) {
   try {
     VoxelGrid grid(device);
     grid.initialize(resolution, Vector4f(min3[0], min3[1], min3[2], 1), Vector4f(max3[0], max3[1], max3[2], 1));
     for (uint32_t p = 0; p < n; ++p)
       grid.insert(Vector4f(points4[4 * p], points4[4 * p + 1], points4[4 * p + 2], points4[4 * p + 3]), labels[p]);
     grid.updateOcclusions();
+    if (insert_occlusion_labels) grid.insertOcclusionLabels();  // the order of the reference's (commented-out) call sites
     for (uint32_t e = 0; e < n_endpoints; ++e) grid.updateInvalid(Vector3f(endpoints3[3 * e], endpoints3[3 * e + 1], endpoints3[3 * e + 2]));
+    if (label_image) std::memcpy(label_image, grid.imageLabel().data(), grid.imageLabel().size() * 2);  // what saveVoxelGrid writes
+    if (bin_image) std::memcpy(bin_image, grid.imageBin().data(), grid.imageBin().size());
+    if (occluded_image) std::memcpy(occluded_image, grid.imageOccluded().data(), grid.imageOccluded().size());
+    if (invalid_image) std::memcpy(invalid_image, grid.imageInvalid().data(), grid.imageInvalid().size());
     if (size3)
       for (int a = 0; a < 3; ++a) size3[a] = grid.size(uint32_t(a));
     if (offset3)

@@ -8,7 +8,7 @@ import voxelizer_b200 as vx
 from oracle.oracle import pack_msb
 
 
-def oracle_frame(orc, cfg_file, scans, labels, poses, prior_idx, past_idx, extra_endpoints=None):
+def oracle_frame(orc, cfg_file, scans, labels, poses, prior_idx, past_idx, extra_endpoints=None, insert_occlusion_labels=False):
     """The loop body of gen_data.cpp:89-121 with the oracle; labels must already be & 0xFFFF."""
     cfg = orc.load_config(cfg_file)
     p = cfg.pod
@@ -24,6 +24,8 @@ def oracle_frame(orc, cfg_file, scans, labels, poses, prior_idx, past_idx, extra
         gt.fill(cfg, anchor, qs, ql, qp)
     gi.update_occlusions()
     gt.update_occlusions()
+    if insert_occlusion_labels:  # gen_data.cpp:108-109 (commented out there), target grid only: VX_FRAME_INSERT_OCCLUSION_LABELS
+        gt.insert_occlusion_labels()
     eps = [orc.endpoint(anchor, poses[i]) for i in past_idx]
     if extra_endpoints is not None:
         eps = list(extra_endpoints)
@@ -59,7 +61,7 @@ def oracle_frame(orc, cfg_file, scans, labels, poses, prior_idx, past_idx, extra
     )
 
 
-def product_frame(backend: vx.Backend, poses, prior_idx, past_idx, extra_endpoints=None, frame_index=0, also=None):
+def product_frame(backend: vx.Backend, poses, prior_idx, past_idx, extra_endpoints=None, frame_index=0, also=None, flags=0):
     """Same frame through vx_process_frames; scans must be resident under their index as id."""
     anchor = poses[prior_idx[-1]]
     ap_p, _ = vx.frame_transforms(anchor, np.stack([poses[i] for i in prior_idx]))
@@ -69,7 +71,7 @@ def product_frame(backend: vx.Backend, poses, prior_idx, past_idx, extra_endpoin
         ap_q, ep = np.zeros((0, 16), np.float32), np.zeros((0, 3), np.float32)
     if extra_endpoints is not None:
         ep = np.asarray(extra_endpoints, np.float32).reshape(-1, 3)
-    spec = vx.FrameSpec(np.asarray(prior_idx, np.uint32), ap_p, np.asarray(past_idx, np.uint32), ap_q, ep)
+    spec = vx.FrameSpec(np.asarray(prior_idx, np.uint32), ap_p, np.asarray(past_idx, np.uint32), ap_q, ep, flags)
     frames = [spec] + list(also or [])
     outs = backend.process(frames)
     o = outs[frame_index]

@@ -30,7 +30,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(vx.GridDesc) == 28
     assert C.sizeof(vx.FilterDesc) == 48
     assert C.sizeof(vx.Options) == 32
-    assert C.sizeof(vx.FrameDesc) == 96
+    assert C.sizeof(vx.FrameDesc) == 104
     assert C.sizeof(vx.GridInfo) == 56
     assert C.sizeof(vx.StageTimes) == 26 * 8
 

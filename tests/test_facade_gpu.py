@@ -115,3 +115,53 @@ def test_voxel_grid_queries_and_public_rays_match_the_reference_grid(orc, shape)
         assert np.array_equal(visited, o_vis), (start, end)
         hits += occluder >= 0
     assert hits > 0
+
+
+@pytest.mark.parametrize("n_endpoints", [0, 3])
+@pytest.mark.parametrize("shape", [((0, -4, -1), (8, 4, 3), 0.5), ((0, -10, -2), (20, 10, 4.4), 0.4)])
+def test_insert_occlusion_labels_matches_the_reference_grid(orc, tmp_path, shape, n_endpoints):
+    """VoxelGrid::insertOcclusionLabels (VoxelGrid.cpp:75-96) in the order of the reference's commented-out call sites
+    (gen_data.cpp:102-116): fill, updateOcclusions, insertOcclusionLabels, updateInvalid x n; every per-voxel query and the
+    four saveVoxelGrid images.  Filled voxels are occupied for the invalid passes and keep invalid_ = min(occluder, own index)."""
+    mn, mx, res = shape
+    rng = np.random.default_rng(7 + n_endpoints)
+    g = orc.grid(res, mn, mx)
+    sx, sy, sz = g.size
+    # structures with empty space below them: blobs in the upper half of the grid, plus a few ground points
+    n = int(g.nvox * 0.03) + 1
+    pts = np.column_stack([rng.uniform(mn[0] + 1, mx[0], n), rng.uniform(mn[1], mx[1], n),
+                           rng.uniform(mn[2] + 0.5 * (mx[2] - mn[2]), mx[2], n), np.ones(n)]).astype(np.float32)
+    ground = np.column_stack([rng.uniform(mn[0], mx[0], n // 3), rng.uniform(mn[1], mx[1], n // 3),
+                              np.full(n // 3, mn[2] + 0.1), np.ones(n // 3)]).astype(np.float32)
+    pts = np.vstack([pts, ground])
+    labels = (rng.integers(1, 6, len(pts)) * 10).astype(np.uint32)
+    eps = np.column_stack([rng.uniform(mn[a], mx[a] + 2, n_endpoints) for a in range(3)]).astype(np.float32).reshape(-1, 3)
+    g.insert(pts, labels)
+    g.update_occlusions()
+    before = int((g.counts() > 0).sum())
+    g.insert_occlusion_labels()
+    assert int((g.counts() > 0).sum()) > before + 20          # the case does fill voxels
+    for e in eps:
+        g.update_invalid(e)
+    occ_o, inv_o = g.flags()
+    got = voxel_grid_probe(res, mn, mx, pts, labels, eps, g.nvox, insert_occlusion_labels=True)
+    assert np.array_equal(got["count"], g.counts())
+    h = g.hist()
+    assert np.array_equal(got["n_labels"], np.bincount(h[:, 0], minlength=g.nvox))
+    best = np.zeros(g.nvox, np.uint32)
+    lab = np.zeros(g.nvox, np.uint32)
+    for v, l, c in h:
+        if c > best[v]:
+            best[v], lab[v] = c, l
+    assert np.array_equal(got["majority"], lab)
+    assert np.array_equal(g.to_output_order(got["occluded"]), occ_o)
+    assert np.array_equal(g.to_output_order(got["invalid"]), inv_o)
+    assert inv_o.sum() > 0
+    # the files saveVoxelGrid writes for this grid in both modes
+    g.save(str(tmp_path), "f", "input")
+    g.save(str(tmp_path), "f", "target")
+    img = got["images"]
+    assert np.array_equal(img["label"], np.fromfile(str(tmp_path / "f.label"), np.uint16))
+    assert np.array_equal(img["bin"], np.fromfile(str(tmp_path / "f.bin"), np.uint8))
+    assert np.array_equal(img["occluded"], np.fromfile(str(tmp_path / "f.occluded"), np.uint8))
+    assert np.array_equal(img["invalid"], np.fromfile(str(tmp_path / "f.invalid"), np.uint8))

@@ -454,3 +454,28 @@ def test_thousand_frame_job_is_deterministic():
         assert not (inv & (o["label"] > 0)).any() and not (inv & ~occl).any() and ((o["label"] > 0) <= occl).all()
         assert inv.sum() > 0
     be.close()
+
+
+def test_frame_flag_insert_occlusion_labels(orc, tmp_path, vis_mode):
+    """VX_FRAME_INSERT_OCCLUSION_LABELS through the C ABI on a real two-grid frame: the target grid is filled between
+    updateOcclusions and the updateInvalid passes (gen_data.cpp:108-109), the input grid's `.bin` is left as inserted."""
+    seq = make_sequence(str(tmp_path / "seq"), 6, 32, 600)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    be = vx.Backend.from_config(vx.Config(cfg_path("example")), debug=True, vis_mode=vis_mode, occlusion_labels=True)
+    for t, (s_, l_) in enumerate(zip(scans, raw)):
+        be.upload_scan(t, s_, l_)
+    o = oracle_frame(orc, cfg_path("example"), scans, labels, poses, [1], [2, 3, 4, 5], insert_occlusion_labels=True)
+    p = product_frame(be, poses, [1], [2, 3, 4, 5], flags=vx.FRAME_INSERT_OCCLUSION_LABELS)
+    assert_frames_equal(p, o, what=("label", "bin", "occluded", "invalid", "occluded_packed", "invalid_packed"))
+    plain = oracle_frame(orc, cfg_path("example"), scans, labels, poses, [1], [2, 3, 4, 5])
+    assert (o["label"] != plain["label"]).sum() > 100            # the flag did something
+    src = be.dump(0, vx.DUMP_FILL_SOURCE)
+    assert int((src != 0xFFFFFFFF).sum()) == int(o["occupancy"].sum()) - int(plain["occupancy"].sum())
+    # without the option the flag is refused
+    be2 = vx.Backend.from_config(vx.Config(cfg_path("example")))
+    for t, (s_, l_) in enumerate(zip(scans, raw)):
+        be2.upload_scan(t, s_, l_)
+    with pytest.raises(vx.VxError, match="occlusion_labels"):
+        product_frame(be2, poses, [1], [2, 3, 4, 5], flags=vx.FRAME_INSERT_OCCLUSION_LABELS)
+    be.close()
+    be2.close()

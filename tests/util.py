@@ -103,7 +103,7 @@ def callers_lib():
         L.vxt_gen_data_frame_by_frame.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int64, C.POINTER(C.c_uint64)]
         L.vxt_build_voxel_grids.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int] + [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p, C.POINTER(C.c_double)]
         L.vxt_voxel_grid_probe.argtypes = ([C.c_int, C.c_float] + [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p, C.c_uint32] + [C.c_void_p] * 8 +
-                                           [C.c_uint32] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p])
+                                           [C.c_uint32] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_int] + [C.c_void_p] * 4)
         _callers = L
     return _callers
 
@@ -140,7 +140,8 @@ def build_voxel_grids(cfg: str, seq_dir: str, target: int, nvox: int, device: in
                 seconds=sec.value)
 
 
-def voxel_grid_probe(resolution, min_extent, max_extent, points4, labels, endpoints, nvox: int, rays=(), device: int = 0) -> dict:
+def voxel_grid_probe(resolution, min_extent, max_extent, points4, labels, endpoints, nvox: int, rays=(), device: int = 0,
+                     insert_occlusion_labels: bool = False) -> dict:
     """vxb::VoxelGrid used directly (raw insert, updateOcclusions, updateInvalid, every per-voxel query, public
     occludedBy rays).  Per-voxel arrays come back in the reference's internal index order i + j*Sx + k*Sx*Sy.
     rays: list of ((i, j, k), (ex, ey, ez))."""
@@ -153,6 +154,8 @@ def voxel_grid_probe(resolution, min_extent, max_extent, points4, labels, endpoi
     size, off = np.zeros(3, np.uint32), np.zeros(3, np.float32)
     out = {k: np.zeros(nvox, np.uint8) for k in ("occluded", "free", "invalid")}
     out.update({k: np.zeros(nvox, np.uint32) for k in ("count", "n_labels", "majority")})
+    images = dict(label=np.zeros(nvox, np.uint16), bin=np.zeros(nvox // 8, np.uint8), occluded=np.zeros(nvox // 8, np.uint8),
+                  invalid=np.zeros(nvox // 8, np.uint8))
     n_rays = len(rays)
     rs = np.ascontiguousarray([r[0] for r in rays], np.int32).reshape(-1, 3)
     re_ = f32([r[1] for r in rays]).reshape(-1, 3)
@@ -162,10 +165,13 @@ def voxel_grid_probe(resolution, min_extent, max_extent, points4, labels, endpoi
     offsets = np.zeros(n_rays + 1, np.uint64)
     rc = L.vxt_voxel_grid_probe(device, resolution, _ptr(mn), _ptr(mx), _ptr(pts), _ptr(lab), len(lab), _ptr(ep), len(ep), _ptr(size), _ptr(off),
                                 _ptr(out["occluded"]), _ptr(out["free"]), _ptr(out["invalid"]), _ptr(out["count"]), _ptr(out["n_labels"]),
-                                _ptr(out["majority"]), n_rays, _ptr(rs), _ptr(re_), _ptr(occluder), _ptr(visited), cap, _ptr(offsets))
+                                _ptr(out["majority"]), n_rays, _ptr(rs), _ptr(re_), _ptr(occluder), _ptr(visited), cap, _ptr(offsets),
+                                int(insert_occlusion_labels), _ptr(images["label"]), _ptr(images["bin"]), _ptr(images["occluded"]),
+                                _ptr(images["invalid"]))
     if rc != 0:
         raise RuntimeError(L.vxt_last_error().decode())
     out["size"] = tuple(int(x) for x in size)
     out["offset"] = off
+    out["images"] = images
     out["rays"] = [(int(occluder[r]), visited[int(offsets[r]): int(offsets[r + 1])].copy()) for r in range(n_rays)]
     return out

@@ -31,7 +31,8 @@ C_ABI_SYMBOLS = (
 )
 
 VX_OK = 0
-DUMP_HIST_TARGET, DUMP_HIST_INPUT, DUMP_OCCUPANCY, DUMP_OCCLUDED, DUMP_INVALID = range(5)
+DUMP_HIST_TARGET, DUMP_HIST_INPUT, DUMP_OCCUPANCY, DUMP_OCCLUDED, DUMP_INVALID, DUMP_FILL_SOURCE = range(6)
+FRAME_INSERT_OCCLUSION_LABELS, FRAME_INPUT_IS_TARGET = 1, 2
 
 
 class VxError(RuntimeError):
@@ -52,7 +53,7 @@ class FilterDesc(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("frames_in_flight", C.c_uint32), ("table_log2_capacity", C.c_uint32), ("stream", C.c_void_p),
-                ("debug", C.c_uint32), ("table_sets", C.c_uint32), ("vis_mode", C.c_uint32), ("reserved", C.c_uint32 * 1)]
+                ("debug", C.c_uint32), ("table_sets", C.c_uint32), ("vis_mode", C.c_uint32), ("occlusion_labels", C.c_uint32)]
 
 
 class FrameDesc(C.Structure):
@@ -61,6 +62,7 @@ class FrameDesc(C.Structure):
         ("n_past", C.c_uint32), ("past_ids", C.c_void_p), ("ap_past", C.c_void_p),
         ("n_endpoints", C.c_uint32), ("endpoints", C.c_void_p),
         ("out_bin", C.c_void_p), ("out_label", C.c_void_p), ("out_occluded", C.c_void_p), ("out_invalid", C.c_void_p),
+        ("flags", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -360,6 +362,7 @@ class FrameSpec:
     past_ids: np.ndarray
     ap_past: np.ndarray
     endpoints: np.ndarray
+    flags: int = 0
 
 
 class PinnedBuffer:
@@ -385,7 +388,7 @@ class Backend:
 
     def __init__(self, resolution, min_extent, max_extent, min_range, max_range, hidecar=True, filtered=(), join_pairs=(),
                  device: int = 0, frames_in_flight: int = 0, table_log2_capacity: int = 0, debug: bool = False, stream: int = 0,
-                 table_sets: int = 0, vis_mode: int = 0):
+                 table_sets: int = 0, vis_mode: int = 0, occlusion_labels: bool = False):
         L = cuda_lib()
         gd = GridDesc(resolution=float(resolution))
         for a in range(3):
@@ -397,7 +400,8 @@ class Backend:
                         filtered_labels=self._filtered.ctypes.data if len(self._filtered) else None, n_filtered=len(self._filtered),
                         join_pairs=self._joins.ctypes.data if len(self._joins) else None, n_join_pairs=len(self._joins) // 2)
         op = Options(frames_in_flight=frames_in_flight, table_log2_capacity=table_log2_capacity, stream=stream or None,
-                     debug=1 if debug else 0, table_sets=table_sets, vis_mode=vis_mode)
+                     debug=1 if debug else 0, table_sets=table_sets, vis_mode=vis_mode,
+                     occlusion_labels=1 if occlusion_labels else 0)
         ctx = C.c_void_p()
         rc = L.vx_create(device, C.byref(gd), C.byref(fd), C.byref(op), C.byref(ctx))
         if rc != VX_OK:
@@ -461,6 +465,7 @@ class Backend:
             d.n_prior, d.prior_ids, d.ap_prior = len(pid), pid.ctypes.data, pap.ctypes.data
             d.n_past, d.past_ids, d.ap_past = len(qid), qid.ctypes.data, qap.ctypes.data
             d.n_endpoints, d.endpoints = len(ep), ep.ctypes.data
+            d.flags = int(getattr(f, "flags", 0))
             if outputs is not None:
                 o = outputs[i]
                 d.out_bin, d.out_label = o["bin"].ctypes.data, o["label"].ctypes.data
@@ -521,6 +526,8 @@ class Backend:
         self._check(L.vx_debug_dump(self._ctx, frame_index, kind, None, C.byref(cnt)), "vx_debug_dump")
         if kind in (DUMP_HIST_TARGET, DUMP_HIST_INPUT):
             out = np.zeros((cnt.value, 3), np.uint32)
+        elif kind == DUMP_FILL_SOURCE:
+            out = np.zeros(cnt.value, np.uint32)
         else:
             out = np.zeros(cnt.value, np.uint8)
         if cnt.value:

@@ -101,6 +101,7 @@ struct vx_ctx {
   uint32_t max_slots = 0;   // frames per batch (one visibility launch)
   uint32_t table_sets = 0;  // frames per fill -> vote -> emit launch
   uint32_t log2_target = 18, log2_input = 15;
+  bool occlusion_labels = false;  // vx_options.occlusion_labels: slots and scratch carry the arrays insertOcclusionLabels needs
   int vis_mode = 0;  // 0 by batch size, 1 throughput shape, 2 latency shape (vx_options.vis_mode)
   bool keep_tables = false;
   bool tables_dirty = false;  // tables hold the previous batch (debug mode)
@@ -189,9 +190,15 @@ size_t table_bytes(uint32_t log2_cap) {
 
 size_t table_set_bytes(const vx_ctx* c) { return table_bytes(c->log2_target) + table_bytes(c->log2_input) + 2 * align_up(c->nvox * 8, 256); }
 
-size_t frame_bytes(const vx_ctx* c) { return 6 * align_up((size_t)c->words * 4, 256) + align_up(c->nvox * 2, 256); }
+size_t frame_bytes(const vx_ctx* c) {
+  size_t b = 6 * align_up((size_t)c->words * 4, 256) + align_up(c->nvox * 2, 256);
+  if (c->occlusion_labels) b += align_up((size_t)c->words * 4, 256) + 2 * align_up(c->nvox * 4, 256);
+  return b;
+}
 
-size_t scratch_bytes(const vx_ctx* c) { return align_up(c->nvox * 4, 256) + align_up((c->visits / 32 + 1) * 4, 256); }
+size_t scratch_bytes(const vx_ctx* c) {
+  return align_up(c->nvox * 4, 256) + align_up((c->visits / 32 + 1) * 4, 256) + (c->occlusion_labels ? align_up((c->visits + 32) * 4, 256) : 0);
+}
 
 struct Carver {
   unsigned char* p;
@@ -232,6 +239,12 @@ void carve_frame(vx_ctx* c, uint32_t index, unsigned char* arena) {
   s.dev.out_bin = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
   s.dev.out_occluded = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
   s.dev.out_invalid = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
+  s.dev.occ_filled = s.dev.occluder = s.dev.fill_source = nullptr;
+  if (c->occlusion_labels) {
+    s.dev.occ_filled = reinterpret_cast<uint32_t*>(cv.take((size_t)c->words * 4));
+    s.dev.occluder = reinterpret_cast<uint32_t*>(cv.take(c->nvox * 4));
+    s.dev.fill_source = reinterpret_cast<uint32_t*>(cv.take(c->nvox * 4));
+  }
 }
 
 void free_slots(vx_ctx* c) {
@@ -288,6 +301,7 @@ int ensure_scratch(vx_ctx* c, uint32_t n_frames) {
     Carver cv{static_cast<unsigned char*>(slab) + (i - old) * each};
     c->scratch[i].dev.memo = reinterpret_cast<uint32_t*>(cv.take(c->nvox * 4));
     c->scratch[i].dev.hitbits = reinterpret_cast<uint32_t*>(cv.take((c->visits / 32 + 1) * 4));
+    c->scratch[i].dev.hitcell = c->occlusion_labels ? reinterpret_cast<uint32_t*>(cv.take((c->visits + 32) * 4)) : nullptr;
   }
   std::vector<VxVisScratch> host(want);
   for (size_t i = 0; i < want; ++i) host[i] = c->scratch[i].dev;
@@ -414,8 +428,12 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
           ++ai;
         }
       }
+      if ((fr.flags & VX_FRAME_INSERT_OCCLUSION_LABELS) && !c->occlusion_labels)
+        return fail(c, VX_ERR_INVALID, "VX_FRAME_INSERT_OCCLUSION_LABELS needs a context created with vx_options.occlusion_labels");
       vis[f].n_endpoints = fr.n_endpoints;
       vis[f].endpoint_offset = (uint32_t)ei;
+      vis[f].flags = fr.flags;
+      vis[f].pad = 0;
       if (fr.n_endpoints) std::memcpy(ep + 3 * ei, fr.endpoints, (size_t)fr.n_endpoints * 3 * sizeof(float));
       ei += fr.n_endpoints;
     }
@@ -769,6 +787,7 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
     if (options->table_log2_capacity) c->log2_target = options->table_log2_capacity;
     c->keep_tables = (options->debug & 1u) != 0;
     c->vis_mode = options->vis_mode <= 2u ? (int)options->vis_mode : 0;
+    c->occlusion_labels = options->occlusion_labels != 0;
   }
   if (c->log2_target < 10) c->log2_target = 10;
   if (c->log2_target > 30) c->log2_target = 30;
@@ -1097,6 +1116,13 @@ int vx_debug_dump(vx_ctx* c, uint32_t frame_index, int kind, void* dst, uint64_t
     }
     uint8_t* o = static_cast<uint8_t*>(dst);
     for (uint64_t L = 0; L < c->nvox; ++L) o[L] = (a[L >> 5] >> (L & 31)) & 1u;
+    return VX_OK;
+  }
+  if (kind == VX_DUMP_FILL_SOURCE) {
+    *count = c->nvox;
+    if (!dst) return VX_OK;
+    if (!s.fill_source) return fail(c, VX_ERR_INVALID, "fill-source dump needs vx_options.occlusion_labels");
+    VX_CUDA(c, cudaMemcpy(dst, s.fill_source, c->nvox * 4, cudaMemcpyDeviceToHost));
     return VX_OK;
   }
   return fail(c, VX_ERR_INVALID, "unknown dump kind");

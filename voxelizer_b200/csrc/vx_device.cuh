@@ -40,6 +40,10 @@ struct VxSlot {
   uint32_t* out_occluded;     // [words]
   uint32_t* out_invalid;      // [words]
   unsigned long long* counters;  // [VX_SLOT_STATS] rays, steps, waves, resolve waves, rounds, cycles[8]
+  // insertOcclusionLabels (vx_options.occlusion_labels; null otherwise)
+  uint32_t* occ_filled;       // [words] occupancy after the fill: what the invalid passes see
+  uint32_t* occluder;         // [nvox] pass 0: reference-internal index of the voxel that occludes a free voxel (last visit)
+  uint32_t* fill_source;      // [nvox] L of the voxel a filled voxel copied from, 0xFFFFFFFF otherwise
 };
 
 // Scratch of one RESIDENT visibility CTA (claimed at run time, so the pool is as large as the number
@@ -47,6 +51,7 @@ struct VxSlot {
 struct VxVisScratch {
   uint32_t* memo;     // [nvox]  occludedBy_ as (pass epoch << 25 | id of the latest ray that crossed the cell)
   uint32_t* hitbits;  // [visits / 32 + 1] ray id -> the ray ended on an occupied cell (current pass)
+  uint32_t* hitcell;  // [visits] ray id -> L of that cell (pass 0 of frames with insertOcclusionLabels; null without the option)
 };
 
 // Fill work is organised by SCAN: a tile of a scan is loaded once and inserted into every frame of the
@@ -77,6 +82,8 @@ struct VxFilterDev {
 struct VxVisFrame {
   uint32_t n_endpoints;
   uint32_t endpoint_offset;  // into the batch's endpoint array (3 floats each)
+  uint32_t flags;            // vx_frame_flags
+  uint32_t pad;
 };
 
 __device__ __forceinline__ uint32_t vx_ldcg_u32(const uint32_t* p) { return __ldcg(p); }

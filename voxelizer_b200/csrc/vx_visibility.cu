@@ -37,9 +37,24 @@
 // bitmap of 4x4x1-voxel blocks (5 % of the steps need the exact bit from global memory); leaving the
 // grid is one zero-field test on the packed position (trace_warp).  Global traffic: one memo read per live visit,
 // one fire-and-forget RED per ray step, one hit-bit gather per live visit.
+#include <cstdio>
 #include <type_traits>
 
 #include "vx_launch.h"
+
+// Checked build (-DVX_CHECKED, tools/build_variants.py): every index into shared memory and into the per-frame global
+// arrays is tested and a violation traps (compute-sanitizer is closed on the B200 pool, so the bounds checks are our own).
+#ifdef VX_CHECKED
+#define VX_ASSERT(cond)                                                                               \
+  do {                                                                                                \
+    if (!(cond)) {                                                                                    \
+      printf("VX_ASSERT failed: %s (vx_visibility.cu:%d, block %d thread %d)\n", #cond, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+      __trap();                                                                                       \
+    }                                                                                                 \
+  } while (0)
+#else
+#define VX_ASSERT(cond) ((void)0)
+#endif
 
 namespace {
 
@@ -93,6 +108,9 @@ struct VisShared {
   uint32_t queue;
   uint32_t scratch_id;
   uint32_t maxlen;  // (statistics) longest ray of the wave, in steps
+  // pass 0 of a frame with insertOcclusionLabels (null otherwise; kept here, not in registers: a rare path):
+  uint32_t* hitcell;   // ray id -> L of the cell that stopped it
+  uint32_t* occluder;  // per free cell the reference-internal index of its occluder (last visit wins)
 };
 
 struct Wave {
@@ -125,6 +143,7 @@ struct Frame {
   int32_t ex, ey, ez;  // end voxel of the pass (VoxelGrid.h:99-102: truncation)
   uint32_t pend;       // ... as a packed position; one that cannot be packed (outside the grid) cannot be reached either
   uint32_t epoch;
+  uint32_t nvox, hit_words;  // (bounds of memo / hitbits, for the checked build)
   bool inv;
   bool tables;        // sm.axis holds this pass's ray set-up
 };
@@ -195,6 +214,7 @@ __device__ __forceinline__ int32_t live_rank(const Frame& f, const Wave& w, cons
   if (fx != w.fixed || (uint32_t)col >= (uint32_t)w.ncols) return -1;
   const uint32_t c = (uint32_t)col * (uint32_t)f.cpc + ((uint32_t)k >> 5);
   const uint32_t bit = (uint32_t)k & 31u;
+  VX_ASSERT(c < (uint32_t)C::kMaxChunks);
   const uint32_t m = sm.chmask[c];
   if (!((m >> bit) & 1u)) return -1;
   return (int32_t)((uint32_t)sm.chbase[c] + (uint32_t)__popc(m & ((1u << bit) - 1u)));
@@ -355,9 +375,11 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared<C>& sm, uint
       const bool a0 = lt01 && lt02;
       const bool a1 = !lt01 && lt12;
       const int32_t x = live_rank(f, w, sm, (int32_t)(P & kPosMaskIJ), (int32_t)((P >> kPosJ) & kPosMaskIJ), (int32_t)(P >> kPosK));
+      VX_ASSERT(x < C::kMaxLive);
       if (x >= (int32_t)rc) atomicMax(&sm.owner[x], kSet | (tag & kIdMask));
       in_face = !(normal == 0 ? a0 : a1);
     }
+    VX_ASSERT(!act || L < f.nvox);
     uint32_t* const mark = f.memo + L;
     asm volatile(
         "{\n\t"
@@ -408,7 +430,9 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared<C>& sm, uint
         if (act == 0u && mine < take) {
           const uint32_t s = base + mine;
           if (s < n_cast) {
+            VX_ASSERT(s < (uint32_t)C::kMaxLive);
             rc = sm.cand[s];
+            VX_ASSERT(rc < (uint32_t)C::kMaxLive);
             tag = enc_epoch | (id_base + s);
             int32_t i, j, k;
             wave_cell(f, w, sm.rcell[rc], i, j, k);
@@ -462,9 +486,14 @@ __device__ void trace_warp(const Frame& f, const Wave& w, VisShared<C>& sm, uint
     bool done = false;
     if (attn) {
       bool hit = false;
+      VX_ASSERT(fin || L < f.nvox);
       if (!fin) hit = (__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u;  // ~5 % of the steps: the exact bit decides
       if (fin || hit) {
-        if (hit) vx_red_or(&f.hitbits[(tag & kIdMask) >> 5], 1u << (tag & 31u));
+        VX_ASSERT(((tag & kIdMask) >> 5) < f.hit_words);
+        if (hit) {
+          vx_red_or(&f.hitbits[(tag & kIdMask) >> 5], 1u << (tag & 31u));
+          if (sm.hitcell) sm.hitcell[tag & kIdMask] = L;
+        }
 #ifdef VX_TRACE_STATS
         atomicMax(&sm.maxlen, len);
 #endif
@@ -530,6 +559,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
     for (int u = 0; u < C::kChunksPerThread; ++u) {
       const uint32_t c = tid * C::kChunksPerThread + (uint32_t)u;
       if (c < n_chunks) {
+        VX_ASSERT(c < (uint32_t)C::kMaxChunks);
         sm.chmask[c] = masks[u];
         sm.chbase[c] = (uint16_t)(run < 0xFFFFu ? run : 0xFFFFu);
         run += (uint32_t)__popc(masks[u]);
@@ -558,6 +588,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       while (m) {
         const uint32_t b = (uint32_t)__ffs(m) - 1u;
         m &= m - 1u;
+        VX_ASSERT(r < (uint32_t)C::kMaxLive);
         sm.rcell[r++] = (uint16_t)((c << 5) | b);
       }
     }
@@ -575,6 +606,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
     if (r < r_end) {
       int32_t i, j, k;
       wave_cell(f, w, sm.rcell[r], i, j, k);
+      VX_ASSERT(lin(f.g, i, j, k) < f.nvox);
       m[u] = __ldcg(f.memo + lin(f.g, i, j, k));
     }
   }
@@ -594,7 +626,10 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
   uint32_t cslot = block_scan(sm, (uint32_t)__popc(cand_flags));
 #pragma unroll
   for (int u = 0; u < C::kLivePerThread; ++u)
-    if ((cand_flags >> u) & 1u) sm.cand[cslot++] = (uint16_t)(r_begin + (uint32_t)u);
+    if ((cand_flags >> u) & 1u) {
+      VX_ASSERT(cslot < (uint32_t)C::kMaxLive);
+      sm.cand[cslot++] = (uint16_t)(r_begin + (uint32_t)u);
+    }
   if (tid < C::kMaxLive / 32) {
     sm.killed[tid] = 0;
     sm.decided[tid] = 0;
@@ -624,6 +659,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       if (normal_first(f, sm, i, j, k, normal)) continue;
       bool any = false;
       prefix_walk(f, w, sm, rc, [&](uint32_t x) {
+        VX_ASSERT(x < (uint32_t)C::kMaxLive);
         if (!(sm.owner[x] & kSet)) {
           atomicAdd(&sm.owner[x], 1u);
           any = true;
@@ -740,6 +776,7 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       hw[u] = 0;
       if (r < n_live) {
         own[u] = sm.owner[r];
+        VX_ASSERT(!(own[u] & kSet) || ((own[u] & kIdMask) >> 5) < f.hit_words);
         if (own[u] & kSet) hw[u] = __ldcg(f.hitbits + ((own[u] & kIdMask) >> 5));
       }
     }
@@ -755,8 +792,17 @@ __device__ int32_t run_wave(const Frame& f, int32_t face, int32_t fixed, int32_t
       if (f.inv) {
         vx_red_and(&f.live[L >> 5], ~(1u << (L & 31u)));  // invalid_ = -1, for good
       } else {
-        if (hit) vx_red_or(&f.occl[L >> 5], 1u << (L & 31u));  // last visit wins
-        else vx_red_and(&f.occl[L >> 5], ~(1u << (L & 31u)));
+        if (hit) {
+          vx_red_or(&f.occl[L >> 5], 1u << (L & 31u));  // last visit wins
+          if (sm.hitcell) {  // insertOcclusionLabels needs occlusions_ itself (the occluder's index), not just "> -1"
+            const uint32_t Lh = __ldcg(sm.hitcell + (own[u] & kIdMask));
+            const uint32_t hk = Lh % (uint32_t)f.g.nz, hij = Lh / (uint32_t)f.g.nz;
+            const uint32_t hj = hij % (uint32_t)f.g.ny, hi = hij / (uint32_t)f.g.ny;
+            sm.occluder[L] = hi + hj * (uint32_t)f.g.nx + hk * (uint32_t)f.g.nx * (uint32_t)f.g.ny;
+          }
+        } else {
+          vx_red_and(&f.occl[L >> 5], ~(1u << (L & 31u)));
+        }
       }
     }
   }
@@ -793,12 +839,16 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
 
   Frame f;
   f.g = g;
+  f.nvox = nvox;
+  f.hit_words = hit_words;
   f.cpc = (g.nz + 31) >> 5;
   f.occ = slot.occ;
   f.live = slot.alive;
   f.memo = scratch[scratch_id].memo;
   f.hitbits = scratch[scratch_id].hitbits;
   f.occl = slot.occl;
+  // VX_FRAME_INSERT_OCCLUSION_LABELS (re-read where it is needed: a rare path must not cost the common one a register)
+  auto fill_labels_on = [&]() { return (frames[blockIdx.x].flags & 1u) != 0u && slot.occ_filled != nullptr; };
   // coarse bitmap geometry: the smallest block size whose power-of-two padded bitmap fits
   const uint32_t kw = (uint32_t)((g.nz + 31) >> 5);
   uint32_t lkw = 0;
@@ -870,6 +920,11 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
                  ? ((uint32_t)f.ex | ((uint32_t)f.ey << 11) | ((uint32_t)f.ez << 22))
                  : 0xFFFFFFFFu;
     f.epoch = (pass % kMaxEpoch) + 1u;
+    if (tid == 0) {
+      const bool record = pass == 0 && fill_labels_on();
+      sm.hitcell = record ? scratch[scratch_id].hitcell : nullptr;
+      sm.occluder = record ? slot.occluder : nullptr;
+    }
     build_axis_table(f, sm);  // (barrier inside)
     if (pass % kMaxEpoch == 0) {  // first pass, or the epoch counter restarts: forget every memo
       for (uint32_t x = tid; x < nvox; x += C::kThreads) f.memo[x] = 0u;
@@ -890,16 +945,85 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     // the ray ids start again at 0: clear the hit bits this pass used
     const uint32_t used_words = min(hit_words, (id_base + 31u) >> 5);
     for (uint32_t x = tid; x < used_words; x += C::kThreads) f.hitbits[x] = 0;
-    if (pass == 0) {  // invalid_ = occlusions_ (VoxelGrid.cpp:169): what is not occluded is dead from here on
+    if (pass == 0) {
+      const bool fill_labels = fill_labels_on();
+      if (fill_labels) {
+        // VoxelGrid::insertOcclusionLabels (VoxelGrid.cpp:75-96): a voxel that was empty when the occlusions were computed takes
+        // count and labels of the first occupied voxel above it if only occluded empty voxels lie between.  The reference walks
+        // each column bottom-up and looks upwards at counts it has not modified yet: one top-down scan per column with the
+        // ORIGINAL occupancy is the same thing.  Filled voxels are occupied for every pass that follows (occ_filled); occluded
+        // ones keep invalid_ = min(occluder index, own index) (VoxelGrid.cpp:187-190,227): isInvalid iff the occluder's
+        // reference-internal index is the smaller one -- or, without any updateInvalid pass, iff occluded at all.
+        __syncthreads();  // occl is final
+        for (uint32_t x = tid; x < words; x += C::kThreads) {
+          slot.occ_filled[x] = __ldg(f.occ + x);
+          slot.out_invalid[x] = 0u;  // (scratch until the pack kernel: filled voxels that stay invalid)
+        }
+        __syncthreads();
+        const uint32_t none = 0xFFFFFFFFu;
+        for (uint32_t col = tid; col < (uint32_t)g.nx * (uint32_t)g.ny; col += C::kThreads) {
+          const int32_t ci = (int32_t)(col / (uint32_t)g.ny), cj = (int32_t)(col % (uint32_t)g.ny);
+          uint32_t src = none;
+          for (int32_t ck = g.nz - 1; ck >= 0; --ck) {
+            const uint32_t L = lin(g, ci, cj, ck);
+            const bool occupied_here = (__ldg(f.occ + (L >> 5)) >> (L & 31u)) & 1u;
+            const bool occluded_here = (__ldcg(f.occl + (L >> 5)) >> (L & 31u)) & 1u;
+            uint32_t from = none;
+            if (occupied_here) {
+              src = L;
+            } else {
+              from = src;
+              if (!occluded_here) src = none;  // a visible empty voxel ends the run for everything below it
+            }
+            slot.fill_source[L] = from;
+            if (from != none) {
+              slot.out_label[L] = slot.out_label[from];
+              atomicOr(&slot.occ_filled[L >> 5], 1u << (L & 31u));
+              const uint32_t own_index = (uint32_t)ci + (uint32_t)cj * (uint32_t)g.nx + (uint32_t)ck * (uint32_t)g.nx * (uint32_t)g.ny;
+              if (occluded_here && (n_pass == 1u || slot.occluder[L] < own_index)) atomicOr(&slot.out_invalid[L >> 5], 1u << (L & 31u));
+            }
+          }
+        }
+        __syncthreads();
+        f.occ = slot.occ_filled;  // first read from here on (never cached before): what the invalid passes see
+        for (uint32_t x = tid; x < words; x += C::kThreads) {  // the filled voxels join the coarse bitmap
+          const uint32_t added = __ldcg(slot.occ_filled + x) & ~__ldg(slot.occ + x);
+          uint32_t bits = added;
+          while (bits) {
+            const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+            bits &= bits - 1u;
+            const uint32_t L = x * 32u + b;
+            const uint32_t k = L % (uint32_t)g.nz, ij = L / (uint32_t)g.nz;
+            const uint32_t i = ij / (uint32_t)g.ny, j = ij - i * (uint32_t)g.ny;
+            atomicOr(&sm.coarse[coarse_word(f, i, j, k)], 1u << (k & 31u));
+          }
+        }
+      }
+      // invalid_ = occlusions_ (VoxelGrid.cpp:169): what is not occluded is dead from here on
       uint32_t n_live0 = 0, n_occ = 0;
       for (uint32_t x = tid; x < words; x += C::kThreads) {
-        const uint32_t o = __ldg(f.occ + x);
+        const uint32_t o = fill_labels ? __ldcg(slot.occ_filled + x) : __ldg(f.occ + x);
         const uint32_t l = __ldcg(f.occl + x) & ~o;
         f.live[x] = l;
         n_live0 += (uint32_t)__popc(l);
         n_occ += (uint32_t)__popc(o);
       }
       atomicAdd(&slot.counters[12], (unsigned long long)n_live0 | ((unsigned long long)n_occ << 32));  // (statistics)
+    }
+    __syncthreads();
+  }
+
+  if (fill_labels_on()) {  // filled voxels that stay invalid; `.bin` of a grid that is its own input grid
+    for (uint32_t x = tid; x < words; x += C::kThreads) f.live[x] = __ldcg(f.live + x) | slot.out_invalid[x];
+    if (frames[blockIdx.x].flags & 2u) {  // VX_FRAME_INPUT_IS_TARGET
+      for (uint32_t x = tid; x < words; x += C::kThreads) {
+        uint32_t bits = 0u;
+        for (uint32_t b = 0; b < 32u; ++b) {
+          const uint32_t L = x * 32u + b;
+          if (L < nvox && slot.out_label[L] > 0) bits |= 1u << b;
+        }
+        slot.out_bin[x] = __byte_perm(__brev(bits), 0u, 0x0123u);  // MSB-first bytes (voxelize_utils.cpp:205-216)
+      }
     }
     __syncthreads();
   }

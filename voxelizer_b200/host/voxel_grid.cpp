@@ -29,8 +29,8 @@ void VoxelGrid::requireInitialized() const {
   if (!initialized_) throw std::logic_error("VoxelGrid: initialize() has not been called");
 }
 
-void VoxelGrid::ensureContext(const Filter& f) const {
-  if (ctx_ && ctxFilter_ == f) return;
+void VoxelGrid::ensureContext(const Filter& f, bool occlusionLabels) const {
+  if (ctx_ && ctxFilter_ == f && (ctxFill_ || !occlusionLabels)) return;
   if (ctx_) {
     vx_destroy(ctx_);
     ctx_ = nullptr;
@@ -54,8 +54,10 @@ void VoxelGrid::ensureContext(const Filter& f) const {
   vo.frames_in_flight = 1;  // one grid = one frame at a time
   vo.table_sets = 1;
   vo.debug = 1;             // keep the histogram for operator() / voxels()
+  vo.occlusion_labels = occlusionLabels ? 1u : 0u;
   if (vx_create(device_, &gd, &fd, &vo, &ctx_) != VX_OK) fail(nullptr, "vx_create");
   ctxFilter_ = f;
+  ctxFill_ = occlusionLabels;
 }
 
 void VoxelGrid::initialize(float resolution, const Vector4f& min, const Vector4f& max) {
@@ -83,6 +85,7 @@ void VoxelGrid::clear() {
   scans_.clear();
   mode_ = kEmpty;
   occlusions_ = false;
+  fillLabels_ = false;
   endpoints_.clear();
   dirty_ = true;
   voxelsValid_ = false;
@@ -137,6 +140,16 @@ void VoxelGrid::updateOcclusions() {
   dirty_ = true;
 }
 
+void VoxelGrid::insertOcclusionLabels() {
+  requireInitialized();
+  if (fillLabels_) throw std::logic_error("VoxelGrid: insertOcclusionLabels() once per clear()");
+  if (!endpoints_.empty()) throw std::logic_error("VoxelGrid: insertOcclusionLabels() has to come before updateInvalid()");
+  occlusions_ = true;  // if (!occlusionsValid_) updateOcclusions();  (VoxelGrid.cpp:76)
+  fillLabels_ = true;
+  dirty_ = true;
+  voxelsValid_ = false;
+}
+
 void VoxelGrid::updateInvalid(const Vector3f& position) {
   requireInitialized();
   occlusions_ = true;  // the reference needs updateOcclusions() first (invalid_ = occlusions_, VoxelGrid.cpp:169)
@@ -147,7 +160,7 @@ void VoxelGrid::updateInvalid(const Vector3f& position) {
 void VoxelGrid::flush() const {
   requireInitialized();
   if (!dirty_) return;
-  if (mode_ != kEmpty) ensureContext(filter_);  // an empty grid keeps whatever context initialize() made
+  if (mode_ != kEmpty || fillLabels_) ensureContext(mode_ != kEmpty ? filter_ : ctxFilter_, fillLabels_);  // (an empty grid keeps initialize()'s context)
   if (vx_evict_all(ctx_) != VX_OK) fail(ctx_, "vx_evict_all");
   const uint32_t n = uint32_t(scans_.size());
   std::vector<uint32_t> ids(n);
@@ -179,6 +192,7 @@ void VoxelGrid::flush() const {
   d.out_label = label_.data();
   d.out_occluded = occludedImg_.data();
   d.out_invalid = invalidImg_.data();
+  if (fillLabels_) d.flags = VX_FRAME_INSERT_OCCLUSION_LABELS | VX_FRAME_INPUT_IS_TARGET;  // this grid is its own input grid
   if (vx_process_frames(ctx_, &d, 1) != VX_OK) fail(ctx_, "vx_process_frames");
   uint64_t count = 0;
   occludedFlag_.assign(nvox, 0);
@@ -204,6 +218,16 @@ const std::vector<VoxelGrid::Voxel>& VoxelGrid::voxels() const {
       Voxel& v = voxels_[size_t(index(int32_t(i), int32_t(j), int32_t(k)))];
       v.labels[label] += c;
       v.count += c;
+    }
+    if (fillLabels_) {  // filled voxels hold a copy of their source voxel (VoxelGrid.cpp:90-91); sources are never filled themselves
+      std::vector<uint32_t> src(num_elements());
+      if (vx_debug_dump(ctx_, 0, VX_DUMP_FILL_SOURCE, src.data(), &count) != VX_OK) fail(ctx_, "vx_debug_dump");
+      auto internal = [&](uint32_t L) {
+        const uint32_t k = L % sizez_, ij = L / sizez_;
+        return size_t(index(int32_t(ij / sizey_), int32_t(ij % sizey_), int32_t(k)));
+      };
+      for (uint32_t L = 0; L < num_elements(); ++L)
+        if (src[L] != 0xFFFFFFFFu) voxels_[internal(L)] = voxels_[internal(src[L])];
     }
     voxelsValid_ = true;
   }

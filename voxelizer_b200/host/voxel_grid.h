@@ -19,6 +19,9 @@
 //     reference would let later passes see the new points; no caller does that).
 //   * insert() (raw, already transformed points) and fillVoxelGrid() (scan + pose + Config filters) cannot
 //     be mixed on one grid between two clear() calls: std::logic_error.
+//   * insertOcclusionLabels() (dead code in the reference: both call sites are commented out, gen_data.cpp:108-109,
+//     Mainframe.cpp:303-304) is offered in the order those call sites use -- after the fills, before any updateInvalid(),
+//     once per clear(); anything else throws std::logic_error.
 //   * occludedBy() is the PUBLIC method (VoxelGrid.h:89-90): one ray on the device over the grid's occupancy, same
 //     return value and visited list; its memo side effect is not observable through the public API (both passes
 //     reset occludedBy_ before reading it) and does not exist here.
@@ -73,6 +76,8 @@ class VoxelGrid {
 
   void updateOcclusions();
   void updateInvalid(const Vector3f& position);
+  /** fill occluded voxels with the labels of the occupied voxel above them (VoxelGrid.cpp:75-96) */
+  void insertOcclusionLabels();
 
   /** ray from voxel (i,j,k) towards `endpoint`: index() of the occupied voxel that stops it or -1; `visited` receives
    *  every voxel the ray looks at, the occluder included (VoxelGrid.h:89-90, VoxelGrid.cpp:235-316) */
@@ -110,7 +115,7 @@ class VoxelGrid {
     std::vector<float> xyzr;
     std::vector<uint32_t> labels;
   };
-  void ensureContext(const Filter& f) const;
+  void ensureContext(const Filter& f, bool occlusionLabels = false) const;
   void flush() const;
   void requireInitialized() const;
 
@@ -125,11 +130,13 @@ class VoxelGrid {
   Filter filter_{};
   std::vector<PendingScan> scans_;  // kScans: one per fillVoxelGrid scan; kRaw: scans_[0] collects insert() points
   bool occlusions_{false};
+  bool fillLabels_{false};  // insertOcclusionLabels() was called
   std::vector<Vector3f> endpoints_;
 
   // device side + cached results
   mutable vx_ctx* ctx_{nullptr};
   mutable Filter ctxFilter_{};
+  mutable bool ctxFill_{false};
   mutable bool dirty_{true};
   mutable std::vector<uint8_t> bin_, occludedImg_, invalidImg_, occludedFlag_, invalidFlag_;
   mutable std::vector<uint16_t> label_;
