@@ -526,6 +526,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     for (uint32_t f = f0; f < f1; ++f) {
       const vx_frame_desc& fr = frames[f];
       if (!fr.out_label && !fr.out_bin) continue;
+      if (fr.flags & VX_FRAME_INSERT_OCCLUSION_LABELS) continue;  // its labels change during the traversal: copied below
       if (first) {
         VX_CUDA(c, cudaStreamWaitEvent(c->copy_out, c->ev_sub[4 * g + 3], 0));
         first = false;
@@ -539,6 +540,10 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   for (uint32_t f = 0; f < nb; ++f) {
     const vx_frame_desc& fr = frames[f];
     const VxSlot& s = c->slots[f].dev;
+    if (fr.flags & VX_FRAME_INSERT_OCCLUSION_LABELS) {
+      if (fr.out_label) VX_CUDA(c, cudaMemcpyAsync(fr.out_label, s.out_label, (size_t)c->nvox * 2, cudaMemcpyDeviceToHost, st));
+      if (fr.out_bin) VX_CUDA(c, cudaMemcpyAsync(fr.out_bin, s.out_bin, packed, cudaMemcpyDeviceToHost, st));
+    }
     if (fr.out_occluded) VX_CUDA(c, cudaMemcpyAsync(fr.out_occluded, s.out_occluded, packed, cudaMemcpyDeviceToHost, st));
     if (fr.out_invalid) VX_CUDA(c, cudaMemcpyAsync(fr.out_invalid, s.out_invalid, packed, cudaMemcpyDeviceToHost, st));
   }
