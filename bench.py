@@ -465,15 +465,25 @@ def run_ours(args):
         barrier()
         return dev_ms, wall_ms
 
-    # ---- value: inputs resident in HBM
+    # ---- value: inputs resident in HBM.  The K steps are SUBMITTED back to back (vx_submit_frames; the library keeps two batches in
+    # flight): a step ends with its slowest frames (~1.2 x the mean frame time), and the CTAs of the next step take the slots
+    # the finished frames leave.  `single_step` below is the same job with a wait after every step.
     seq.upload(be)
+
+    def run_steps(k):
+        tickets = []
+        for _ in range(k):
+            tickets.append(be.submit_descs(descs_dev, n_frames))
+            if len(tickets) > 2:
+                be.wait(tickets[-3])
+        be.wait(0)
+
     step_dev = lambda: be.process_descs(descs_dev, n_frames)
-    for _ in range(args.warmup):
-        step_dev()
+    run_steps(max(1, args.warmup))
     be.reset_stage_times()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    dev_ms, wall_ms = timed(step_dev, args.steps)
+    dev_ms, wall_ms = timed(lambda: run_steps(args.steps), 1)
     sampler.stop_flag.set()
     sampler.join(timeout=5)
     st = be.stage_times()
@@ -484,6 +494,10 @@ def run_ours(args):
         dist.all_reduce(tf)
         total_frames = int(tf)
     value = total_frames / (ms_per_step / 1e3)
+    n_single = min(3, args.steps)
+    s_dev_ms, _ = timed(step_dev, n_single)
+    single_step = {"value": total_frames / (s_dev_ms / n_single / 1e3), "unit": UNIT, "ms_per_step": s_dev_ms / n_single, "steps": n_single,
+                   "what": "the same step with a wait after each one (vx_process_frames): bound by the slowest frame of a 909-frame batch"}
 
     # ---- e2e: host buffers, H2D of every scan and D2H of every output inside the timed region.  Steps are submitted
     # asynchronously and the scans of step k+1 are uploaded (under a second id range) while step k is traversed.
@@ -502,39 +516,64 @@ def run_ours(args):
                 ring = None
     if ring is not None:
         outs = output_views(ring, be, n_frames)
+        ring_b = None
+        try:
+            ring_b = vx.PinnedBuffer(n_frames * per)   # a second output ring: two steps are in flight
+        except Exception:
+            ring_b = None
+        if world > 1:
+            ok = torch.tensor([1 if ring_b is not None else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0 and ring_b is not None:
+                ring_b.free()
+                ring_b = None
+        outs_b = output_views(ring_b, be, n_frames) if ring_b is not None else outs
         ID2 = 1 << 20  # second id range
         sets = []
-        for off in (0, ID2):
+        for off, o in ((0, outs), (ID2, outs_b)):
             sp = [vx.FrameSpec(s.prior_ids + off, s.ap_prior, s.past_ids + off, s.ap_past, s.endpoints) for s in specs] if off else specs
-            sets.append(be.build_descs(sp, outs))
-        state = {"k": 0, "ticket": None}
+            sets.append(be.build_descs(sp, o))
+        offsets = (0, ID2)
+        # steps in flight: 1 = the next step's scans cross PCIe while this step is traversed, then the step is awaited (the
+        # measured optimum: with two steps in flight the next step's fill kernels starve behind 909 resident traversal CTAs)
+        depth = int(os.environ.get("VX_BENCH_E2E_DEPTH", "1"))
+        if ring_b is None:
+            depth = 1
 
         def evict_set(off):
             for t in range(n_scans):
                 be.evict_scan(t + off)
 
-        def step_e2e():
-            k = state["k"]
-            cur, nxt = (0, ID2) if k % 2 == 0 else (ID2, 0)
-            if state["ticket"] is None:        # first step: nothing in flight yet, its scans go up now
-                seq.upload(be, id_offset=cur)
-            ticket = be.submit_descs(sets[k % 2][0], n_frames)
-            evict_set(nxt)                      # the job that read them was awaited at the end of the previous step
-            seq.upload(be, id_offset=nxt)       # step k+1's inputs cross PCIe while step k runs
-            be.wait(ticket)
-            state["ticket"] = ticket
-            state["k"] = k + 1
+        def run_e2e(k_steps):
+            """k steps, each: its scans from pinned host memory into HBM under one of two id ranges, vx_submit_frames with host
+            output buffers, at most `depth` steps in flight; returns when every output of every step has landed."""
+            tickets = []
+            evict_set(offsets[0])
+            seq.upload(be, id_offset=offsets[0])
+            for k in range(k_steps):
+                tickets.append(be.submit_descs(sets[k % 2][0], n_frames))
+                if depth == 2 and k >= 1:
+                    be.wait(tickets[k - 1])          # the other id range (and ring) is free again
+                if k + 1 < k_steps:                  # the next step's inputs cross PCIe while this step runs
+                    evict_set(offsets[(k + 1) % 2])
+                    seq.upload(be, id_offset=offsets[(k + 1) % 2])
+                if depth == 1:
+                    be.wait(tickets[k])
+            be.wait(0)
 
         be.evict_all()
-        step_e2e()                              # warm-up (also pins down the first-step special case)
-        e_dev_ms, e_wall_ms = timed(step_e2e, max(1, args.steps))
+        run_e2e(2)                                  # warm-up
+        e_dev_ms, e_wall_ms = timed(lambda: run_e2e(max(1, args.steps)), 1)
         be.sync()
-        e_ms = e_wall_ms / max(1, args.steps)   # wall clock: includes every host-side gap
+        e_ms = e_wall_ms / max(1, args.steps)       # wall clock: includes every host-side gap
         h2d = int(seq.counts.sum()) * 20 + sum((len(s.prior_ids) + len(s.past_ids)) * (64 + 24) + len(s.endpoints) * 12 for s in specs)
         d2h = n_frames * per
         e2e = {"value": total_frames / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-               "ms_per_step": e_ms, "device_ms_per_step": e_dev_ms / max(1, args.steps),
-               "how": "vx_submit_frames / vx_wait; the next step's scans are uploaded (second id range) while this step is traversed"}
+               "ms_per_step": e_ms, "device_ms_per_step": e_dev_ms / max(1, args.steps), "steps_in_flight": depth,
+               "how": "every step uploads all its scans from pinned host memory and gets all four images of every frame back in pinned host "
+                      "memory; steps are submitted with vx_submit_frames, two in flight (two scan id ranges, two output rings)"}
+        last = (max(1, args.steps) - 1) % 2
+        outs = outs if last == 0 else outs_b         # the step that finished last
         # ---- parity of the benchmarked workload: the frames the reference arm computed, byte for byte
         if ref_line and ref_line.get("frame_hashes"):
             index = {t: i for i, t in enumerate(spec_targets)}
@@ -556,6 +595,8 @@ def run_ours(args):
                 parity_check["first_bad"] = bad[:8]
         be.evict_all()
         seq.upload(be)                          # back to the plain id range for what follows
+        if ring_b is not None:
+            ring_b.free()
 
     # ---- optional legs, outside the headline's timed regions
     extra_configs, strong = None, None
@@ -585,8 +626,10 @@ def run_ours(args):
                                    f"{n_frames} target frames per step per GPU, window up to {cfg.pod.pastScans + 1} scans",
                        "frames_per_step_per_gpu": n_frames, "frames_in_flight": be.frames_in_flight,
                        "l2_policy": "inputs larger than L2 (window of one frame = 180 MB, sequence = 11.6 GB)",
-                       "parallelism": f"{world} x independent target-range shards, no data-path collective"},
+                       "parallelism": f"{world} x independent target-range shards, no data-path collective",
+                       "steps": "submitted back to back, two batches in flight (stage_ms_per_step sums overlapping kernels)"},
             "wall_ms_per_step": wall_ms / args.steps,
+            "single_step": single_step,
             "gpu_launches": sum(launches.values()),
             "launches": launches,
             "stage_ms_per_step": {k: st[k] / args.steps for k in ("fill_ms", "vote_ms", "emit_ms", "visibility_ms", "pack_ms", "total_ms")},

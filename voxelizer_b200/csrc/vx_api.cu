@@ -2,6 +2,7 @@
 // slots and the batch pipeline  fill -> vote -> emit -> visibility -> pack -> copy-out.
 // Host-side only; the kernels live in vx_fill.cu / vx_visibility.cu.  No CPU fallback anywhere: if
 // CUDA is unusable every entry point reports VX_ERR_NO_DEVICE / VX_ERR_CUDA.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -73,6 +74,27 @@ struct Job {
   std::string error;
 };
 
+// One batch in flight.  Two lanes alternate, so that the next batch (of this or the next job) is filled, voted and
+// already tracing while the slowest frames of the previous one finish: a batch ends with its slowest frame (~1.2 x the mean
+// frame time), and CTAs of the next launch take the slots the finished frames leave.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5]{};               // EV_BEGIN .. EV_END
+  std::vector<cudaEvent_t> ev_sub;   // 4 per fill -> vote -> emit launch
+  unsigned char* h_stage = nullptr;  // batch staging (items, ap, endpoints, vis frames): pinned host + device mirror
+  unsigned char* d_stage = nullptr;
+  size_t stage_cap = 0;
+  uint32_t slot_base = 0;            // its frames use slots slot_base .. slot_base + nb - 1
+  // the batch
+  bool busy = false;
+  uint64_t seq = 0;                  // enqueue order
+  const vx_frame_desc* frames = nullptr;
+  uint32_t nb = 0, n_sub = 0;
+  uint64_t points = 0, fill_launches = 0;
+  Job* job = nullptr;                // the job the batch belongs to
+  std::unique_ptr<Job> owned;        // ... owned here if this is the job's last batch
+};
+
 thread_local std::string* tl_error_sink = nullptr;  // set on the worker thread: errors belong to the job, not the context
 
 struct NvtxRange {  // per-stage ranges on the host side of a batch (Stopwatch tic/toc -> NVTX)
@@ -115,7 +137,6 @@ struct vx_ctx {
   VxSlot* d_slots = nullptr;
   uint32_t* d_counters = nullptr;  // max_slots * kCounterWords
   uint32_t* h_counters = nullptr;  // pinned mirror
-  std::vector<cudaEvent_t> ev_sub;  // 4 per fill -> vote -> emit launch
 
   // copy streams: uploads, and the outputs that are final before the traversal starts
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -124,14 +145,15 @@ struct vx_ctx {
   std::vector<UploadMark> marks;      // in upload order; completed ones are recycled
   std::vector<cudaEvent_t> ev_pool;   // timing-less events
 
-  // batch staging (items, ap, endpoints, vis frames): pinned host + device mirror
-  unsigned char* h_stage = nullptr;
-  unsigned char* d_stage = nullptr;
-  size_t stage_cap = 0;
+  Lane lanes[2];            // lanes[0].stream == stream
+  uint32_t depth = 1;       // batches in flight at a time (2 unless the tables are kept for debugging or memory is short)
+  uint32_t lane_cap = 0;    // frames per batch
+  uint32_t next_lane = 0;
+  uint64_t batch_seq = 0;
+  std::vector<uint8_t> slot_ready;  // frame record allocated?
 
-  cudaEvent_t ev[EV_COUNT]{};
   vx_stage_times times{};
-  uint32_t last_batch = 0;
+  uint32_t last_batch = 0, last_base = 0;
   std::string error;
 
   // Asynchronous jobs (vx_submit_frames / vx_wait): one worker thread runs them in submission order.  `mu` guards
@@ -225,7 +247,8 @@ void carve_table_set(vx_ctx* c, TableSet& t, unsigned char* arena) {
 void carve_frame(vx_ctx* c, uint32_t index, unsigned char* arena) {
   FrameRec& s = c->slots[index];
   Carver cv{arena};
-  const TableSet& t = c->tables[index % c->table_sets];
+  // (the histogram tables a frame uses depend on its place IN ITS BATCH, whichever lane runs the batch)
+  const TableSet& t = c->tables[(index % c->lane_cap) % c->table_sets];
   uint32_t* cnt = c->d_counters + (size_t)index * kCounterWords;
   s.dev.target = t.target;
   s.dev.target.overflow = cnt + 1;
@@ -251,12 +274,14 @@ void free_slots(vx_ctx* c) {
   for (void* p : c->slot_slabs) cudaFree(p);
   c->slot_slabs.clear();
   c->slots.clear();
+  c->slot_ready.clear();
   c->tables.clear();
   c->tables_dirty = false;
 }
 
-// One cudaMalloc per growth step (a whole sequence needs ~900 frame records: one call, not 900).
-int ensure_slots(vx_ctx* c, uint32_t n) {
+// One cudaMalloc per growth step (a whole sequence needs ~900 frame records: one call, not 900).  Frame records of the slots
+// base .. base + n - 1 (a lane's range), and one table set per frame of a fill group.
+int ensure_slots(vx_ctx* c, uint32_t base, uint32_t n) {
   const uint32_t want_sets = n < c->table_sets ? n : c->table_sets;
   if (c->tables.size() < want_sets) {
     const size_t old = c->tables.size(), add = want_sets - old, each = table_set_bytes(c);
@@ -264,20 +289,29 @@ int ensure_slots(vx_ctx* c, uint32_t n) {
     VX_CUDA(c, cudaMalloc(&slab, add * each));
     c->slot_slabs.push_back(slab);
     VX_CUDA(c, cudaMemsetAsync(slab, 0, add * each, c->stream));  // all-zero = empty (vote / emit leave them empty again)
+    VX_CUDA(c, cudaStreamSynchronize(c->stream));
     c->tables.resize(want_sets);
     for (size_t i = 0; i < add; ++i) carve_table_set(c, c->tables[old + i], static_cast<unsigned char*>(slab) + i * each);
+    // (records carved earlier keep pointing at their set: index % table_sets is stable while table_sets is)
   }
-  if (c->slots.size() >= n) return VX_OK;
-  const size_t old = c->slots.size(), add = n - old, each = frame_bytes(c);
+  if (c->slots.size() < c->max_slots) {
+    c->slots.resize(c->max_slots);
+    c->slot_ready.assign(c->max_slots, 0);
+  }
+  uint32_t first = base;
+  while (first < base + n && c->slot_ready[first]) ++first;
+  if (first == base + n) return VX_OK;
+  const size_t add = base + n - first, each = frame_bytes(c);
   void* slab = nullptr;
   VX_CUDA(c, cudaMalloc(&slab, add * each));
   c->slot_slabs.push_back(slab);
-  c->slots.resize(n);
-  for (size_t i = 0; i < add; ++i) carve_frame(c, (uint32_t)(old + i), static_cast<unsigned char*>(slab) + i * each);
-  std::vector<VxSlot> host(n);
-  for (size_t i = 0; i < n; ++i) host[i] = c->slots[i].dev;
-  VX_CUDA(c, cudaMemcpyAsync(c->d_slots, host.data(), n * sizeof(VxSlot), cudaMemcpyHostToDevice, c->stream));
-  VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<VxSlot> host(add);
+  for (size_t i = 0; i < add; ++i) {
+    carve_frame(c, (uint32_t)(first + i), static_cast<unsigned char*>(slab) + i * each);
+    c->slot_ready[first + i] = 1;
+    host[i] = c->slots[first + i].dev;
+  }
+  VX_CUDA(c, cudaMemcpy(c->d_slots + first, host.data(), add * sizeof(VxSlot), cudaMemcpyHostToDevice));
   return VX_OK;
 }
 
@@ -288,9 +322,10 @@ int ensure_scratch(vx_ctx* c, uint32_t n_frames) {
   if (!c->d_scratch) {
     VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_scratch), (size_t)want * sizeof(VxVisScratch)));
     VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_locks), (size_t)want * sizeof(uint32_t)));
-    VX_CUDA(c, cudaMemsetAsync(c->d_locks, 0, (size_t)want * sizeof(uint32_t), c->stream));
+    VX_CUDA(c, cudaMemset(c->d_locks, 0, (size_t)want * sizeof(uint32_t)));
   }
-  if (want > n_frames) want = n_frames;
+  // one batch at a time: at most n_frames CTAs exist; two lanes: CTAs of both launches share the SMs, up to `want` are resident
+  if (c->depth == 1 && want > n_frames) want = n_frames;
   if (c->scratch.size() >= want) return VX_OK;
   const size_t old = c->scratch.size(), each = scratch_bytes(c);
   void* slab = nullptr;
@@ -305,22 +340,21 @@ int ensure_scratch(vx_ctx* c, uint32_t n_frames) {
   }
   std::vector<VxVisScratch> host(want);
   for (size_t i = 0; i < want; ++i) host[i] = c->scratch[i].dev;
-  VX_CUDA(c, cudaMemcpyAsync(c->d_scratch, host.data(), (size_t)want * sizeof(VxVisScratch), cudaMemcpyHostToDevice, c->stream));
-  VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  VX_CUDA(c, cudaMemcpy(c->d_scratch, host.data(), (size_t)want * sizeof(VxVisScratch), cudaMemcpyHostToDevice));
   return VX_OK;
 }
 
-int ensure_stage(vx_ctx* c, size_t bytes) {
-  if (bytes <= c->stage_cap) return VX_OK;
-  if (c->h_stage) cudaFreeHost(c->h_stage);
-  if (c->d_stage) cudaFree(c->d_stage);
-  c->h_stage = nullptr;
-  c->d_stage = nullptr;
-  c->stage_cap = 0;
+int ensure_stage(vx_ctx* c, Lane& ln, size_t bytes) {
+  if (bytes <= ln.stage_cap) return VX_OK;
+  if (ln.h_stage) cudaFreeHost(ln.h_stage);
+  if (ln.d_stage) cudaFree(ln.d_stage);
+  ln.h_stage = nullptr;
+  ln.d_stage = nullptr;
+  ln.stage_cap = 0;
   const size_t cap = align_up(bytes * 2, 4096);
-  VX_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&c->h_stage), cap));
-  VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->d_stage), cap));
-  c->stage_cap = cap;
+  VX_CUDA(c, cudaMallocHost(reinterpret_cast<void**>(&ln.h_stage), cap));
+  VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&ln.d_stage), cap));
+  ln.stage_cap = cap;
   return VX_OK;
 }
 
@@ -363,10 +397,11 @@ int wait_for_upload(vx_ctx* c, cudaStream_t st, uint64_t seq, bool* waited) {
   return fail(c, VX_ERR_CUDA, "internal: upload without a mark");
 }
 
-// One batch of <= max_slots frames.  Returns VX_ERR_TABLE_OVERFLOW if a histogram table was too small
-// (caller grows the tables and retries).
-int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
-  int rc = ensure_slots(c, nb);
+// Enqueues one batch of <= lane_cap frames on a lane: stage, fill -> vote -> emit per group, ONE traversal launch, pack, the
+// copies out.  Returns without waiting for the device (unless an output buffer is pageable memory: such a copy blocks).
+int enqueue_batch(vx_ctx* c, Lane& ln, Lane& other, const vx_frame_desc* frames, uint32_t nb) {
+  const uint32_t base = ln.slot_base;
+  int rc = ensure_slots(c, base, nb);
   if (rc != VX_OK) return rc;
   rc = ensure_scratch(c, nb);
   if (rc != VX_OK) return rc;
@@ -391,13 +426,13 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   const size_t off_ep = align_up(off_ap + n_ap * 16 * sizeof(float), 256);
   const size_t off_vis = align_up(off_ep + n_ep * 3 * sizeof(float), 256);
   const size_t total = align_up(off_vis + nb * sizeof(VxVisFrame), 256);
-  rc = ensure_stage(c, total);
+  rc = ensure_stage(c, ln, total);
   if (rc != VX_OK) return rc;
-  VxScanWork* works = reinterpret_cast<VxScanWork*>(c->h_stage + off_works);
-  VxScanUse* uses = reinterpret_cast<VxScanUse*>(c->h_stage + off_uses);
-  float* ap = reinterpret_cast<float*>(c->h_stage + off_ap);
-  float* ep = reinterpret_cast<float*>(c->h_stage + off_ep);
-  VxVisFrame* vis = reinterpret_cast<VxVisFrame*>(c->h_stage + off_vis);
+  VxScanWork* works = reinterpret_cast<VxScanWork*>(ln.h_stage + off_works);
+  VxScanUse* uses = reinterpret_cast<VxScanUse*>(ln.h_stage + off_uses);
+  float* ap = reinterpret_cast<float*>(ln.h_stage + off_ap);
+  float* ep = reinterpret_cast<float*>(ln.h_stage + off_ep);
+  VxVisFrame* vis = reinterpret_cast<VxVisFrame*>(ln.h_stage + off_vis);
 
   // Fill work per group of `table_sets` frames, organised by scan: every scan a group touches becomes one
   // VxScanWork with the list of (frame, matrix, both) it goes into.
@@ -460,19 +495,21 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   }
   work_begin[n_sub] = wi;
 
-  cudaStream_t st = c->stream;
+  cudaStream_t st = ln.stream;
   if (c->tables_dirty) {  // debug mode kept the previous batch's tables
-    VX_CUDA(c, vx_launch_table_reset(c->d_slots, c->dirty_slots, st));
+    VX_CUDA(c, vx_launch_table_reset(c->d_slots + c->last_base, c->dirty_slots, st));
     c->tables_dirty = false;
   }
-  VX_CUDA(c, cudaMemcpyAsync(c->d_stage, c->h_stage, total, cudaMemcpyHostToDevice, st));
-  VX_CUDA(c, cudaMemsetAsync(c->d_counters, 0, (size_t)nb * kCounterWords * sizeof(uint32_t), st));
+  VX_CUDA(c, cudaMemcpyAsync(ln.d_stage, ln.h_stage, total, cudaMemcpyHostToDevice, st));
+  VX_CUDA(c, cudaMemsetAsync(c->d_counters + (size_t)base * kCounterWords, 0, (size_t)nb * kCounterWords * sizeof(uint32_t), st));
+  // frames `table_sets` apart share histogram tables, across lanes too: this batch's first fill waits for the other batch's last emit
+  if (other.busy && other.n_sub) VX_CUDA(c, cudaStreamWaitEvent(st, other.ev_sub[4 * (other.n_sub - 1) + 3], 0));
 
-  const VxScanWork* d_works = reinterpret_cast<const VxScanWork*>(c->d_stage + off_works);
-  const VxScanUse* d_uses = reinterpret_cast<const VxScanUse*>(c->d_stage + off_uses);
-  const float* d_ap = reinterpret_cast<const float*>(c->d_stage + off_ap);
-  const float* d_ep = reinterpret_cast<const float*>(c->d_stage + off_ep);
-  const VxVisFrame* d_vis = reinterpret_cast<const VxVisFrame*>(c->d_stage + off_vis);
+  const VxScanWork* d_works = reinterpret_cast<const VxScanWork*>(ln.d_stage + off_works);
+  const VxScanUse* d_uses = reinterpret_cast<const VxScanUse*>(ln.d_stage + off_uses);
+  const float* d_ap = reinterpret_cast<const float*>(ln.d_stage + off_ap);
+  const float* d_ep = reinterpret_cast<const float*>(ln.d_stage + off_ep);
+  const VxVisFrame* d_vis = reinterpret_cast<const VxVisFrame*>(ln.d_stage + off_vis);
 
   // Uploads may still be in flight on the upload stream: each group waits for the newest scan it reads.
   int rc2 = mark_uploads(c);
@@ -480,37 +517,37 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
   prune_marks(c);
 
   // fill -> vote -> emit in groups of `table_sets` frames (frames of different groups share tables)
-  while (c->ev_sub.size() < (size_t)n_sub * 4) {
+  while (ln.ev_sub.size() < (size_t)n_sub * 4) {
     cudaEvent_t e;
     VX_CUDA(c, cudaEventCreate(&e));
-    c->ev_sub.push_back(e);
+    ln.ev_sub.push_back(e);
   }
   uint64_t fill_launches = 0;
   const uint32_t n_scratch = (uint32_t)c->scratch.size();
-  VX_CUDA(c, cudaEventRecord(c->ev[EV_BEGIN], st));
+  VX_CUDA(c, cudaEventRecord(ln.ev[EV_BEGIN], st));
   for (uint32_t g = 0; g < n_sub; ++g) {
     const uint32_t f0 = g * c->table_sets, f1 = f0 + c->table_sets < nb ? f0 + c->table_sets : nb;
     const uint32_t n_works = (uint32_t)(work_begin[g + 1] - work_begin[g]);
     bool waited = false;
     rc2 = wait_for_upload(c, st, sub_need_seq[g], &waited);
     if (rc2 != VX_OK) return rc2;
-    VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 0], st));
-    VX_CUDA(c, vx_launch_fill(d_works + work_begin[g], n_works, sub_max_points[g], d_uses, d_ap, c->d_slots, c->geom, c->filter, st));
-    VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 1], st));
-    VX_CUDA(c, vx_launch_vote(c->d_slots + f0, f1 - f0, c->nvox, st));
-    VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 2], st));
-    VX_CUDA(c, vx_launch_emit(c->d_slots + f0, f1 - f0, c->keep_tables ? 1 : 0, st));
-    VX_CUDA(c, cudaEventRecord(c->ev_sub[4 * g + 3], st));
+    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 0], st));
+    VX_CUDA(c, vx_launch_fill(d_works + work_begin[g], n_works, sub_max_points[g], d_uses, d_ap, c->d_slots + base, c->geom, c->filter, st));
+    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 1], st));
+    VX_CUDA(c, vx_launch_vote(c->d_slots + base + f0, f1 - f0, c->nvox, st));
+    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 2], st));
+    VX_CUDA(c, vx_launch_emit(c->d_slots + base + f0, f1 - f0, c->keep_tables ? 1 : 0, st));
+    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 3], st));
     fill_launches += (n_works + 65534) / 65535;
   }
   // ONE visibility launch per batch.  (Measured: a launch per group on streams of their own, started as soon as the
   // group is filled, is slower -- every launch places its CTAs on the SMs in the same order, so 8 launches of 114
   // CTAs load 114 SMs with 7 CTAs and leave 34 idle; with groups of 148 it still lost 6 % to the single launch.)
-  VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS_BEGIN], st));
-  VX_CUDA(c, vx_launch_visibility(c->d_slots, d_vis, nb, d_ep, c->geom, c->d_scratch, n_scratch, c->d_locks, c->vis_mode, st));
-  VX_CUDA(c, cudaEventRecord(c->ev[EV_VIS], st));
-  VX_CUDA(c, vx_launch_pack(c->d_slots, nb, c->nvox, st));
-  VX_CUDA(c, cudaEventRecord(c->ev[EV_PACK], st));
+  VX_CUDA(c, cudaEventRecord(ln.ev[EV_VIS_BEGIN], st));
+  VX_CUDA(c, vx_launch_visibility(c->d_slots + base, d_vis, nb, d_ep, c->geom, c->d_scratch, n_scratch, c->d_locks, c->vis_mode, st));
+  VX_CUDA(c, cudaEventRecord(ln.ev[EV_VIS], st));
+  VX_CUDA(c, vx_launch_pack(c->d_slots + base, nb, c->nvox, st));
+  VX_CUDA(c, cudaEventRecord(ln.ev[EV_PACK], st));
   lk.unlock();  // everything that reads the scan cache is enqueued; uploads / evictions of OTHER scans may go on
   nvtx_enqueue.armed = false;
   nvtxRangePop();
@@ -528,18 +565,18 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
       if (!fr.out_label && !fr.out_bin) continue;
       if (fr.flags & VX_FRAME_INSERT_OCCLUSION_LABELS) continue;  // its labels change during the traversal: copied below
       if (first) {
-        VX_CUDA(c, cudaStreamWaitEvent(c->copy_out, c->ev_sub[4 * g + 3], 0));
+        VX_CUDA(c, cudaStreamWaitEvent(c->copy_out, ln.ev_sub[4 * g + 3], 0));
         first = false;
         any_early = true;
       }
-      const VxSlot& s = c->slots[f].dev;
+      const VxSlot& s = c->slots[base + f].dev;
       if (fr.out_label) VX_CUDA(c, cudaMemcpyAsync(fr.out_label, s.out_label, (size_t)c->nvox * 2, cudaMemcpyDeviceToHost, c->copy_out));
       if (fr.out_bin) VX_CUDA(c, cudaMemcpyAsync(fr.out_bin, s.out_bin, packed, cudaMemcpyDeviceToHost, c->copy_out));
     }
   }
   for (uint32_t f = 0; f < nb; ++f) {
     const vx_frame_desc& fr = frames[f];
-    const VxSlot& s = c->slots[f].dev;
+    const VxSlot& s = c->slots[base + f].dev;
     if (fr.flags & VX_FRAME_INSERT_OCCLUSION_LABELS) {
       if (fr.out_label) VX_CUDA(c, cudaMemcpyAsync(fr.out_label, s.out_label, (size_t)c->nvox * 2, cudaMemcpyDeviceToHost, st));
       if (fr.out_bin) VX_CUDA(c, cudaMemcpyAsync(fr.out_bin, s.out_bin, packed, cudaMemcpyDeviceToHost, st));
@@ -551,19 +588,38 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     VX_CUDA(c, cudaEventRecord(c->ev_copy_out, c->copy_out));
     VX_CUDA(c, cudaStreamWaitEvent(st, c->ev_copy_out, 0));
   }
-  VX_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, (size_t)nb * kCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  VX_CUDA(c, cudaEventRecord(c->ev[EV_END], st));
-  VX_CUDA(c, cudaStreamSynchronize(st));
+  VX_CUDA(c, cudaMemcpyAsync(c->h_counters + (size_t)base * kCounterWords, c->d_counters + (size_t)base * kCounterWords,
+                             (size_t)nb * kCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  VX_CUDA(c, cudaEventRecord(ln.ev[EV_END], st));
+  ln.busy = true;
+  ln.seq = ++c->batch_seq;
+  ln.frames = frames;
+  ln.nb = nb;
+  ln.n_sub = n_sub;
+  ln.points = points;
+  ln.fill_launches = fill_launches;
+  return VX_OK;
+}
+
+// Waits for the batch on a lane and books its counters and times.  VX_ERR_TABLE_OVERFLOW: a histogram table was too small (the
+// caller grows the tables and runs the batch again: ln.frames / ln.nb stay).  The lane stays `busy` until settle_batch.
+int finish_batch(vx_ctx* c, Lane& ln) {
+  const uint32_t base = ln.slot_base, nb = ln.nb, n_sub = ln.n_sub;
+  const vx_frame_desc* frames = ln.frames;
+  const uint64_t points = ln.points, fill_launches = ln.fill_launches;
+  NvtxRange nvtx_wait("vx:wait");
+  VX_CUDA(c, cudaStreamSynchronize(ln.stream));
   if (c->keep_tables) {
     c->tables_dirty = true;
     c->dirty_slots = nb;
   }
   c->last_batch = nb;
+  c->last_base = base;
 
   bool overflow = false;
   unsigned long long stats[VX_SLOT_STATS] = {0};
   for (uint32_t f = 0; f < nb; ++f) {
-    const uint32_t* w = c->h_counters + (size_t)f * kCounterWords;
+    const uint32_t* w = c->h_counters + (size_t)(base + f) * kCounterWords;
     if (w[1] || w[3]) overflow = true;
     unsigned long long rs[VX_SLOT_STATS];
     std::memcpy(rs, w + 4, sizeof(rs));
@@ -577,7 +633,7 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
     if (FILE* fp = std::fopen(path, "a")) {
       for (uint32_t f = 0; f < nb; ++f) {
         unsigned long long rs[VX_SLOT_STATS];
-        std::memcpy(rs, c->h_counters + (size_t)f * kCounterWords + 4, sizeof(rs));
+        std::memcpy(rs, c->h_counters + (size_t)(base + f) * kCounterWords + 4, sizeof(rs));
         std::fprintf(fp, "%u %u", f, frames[f].n_endpoints);
         for (int k = 0; k < VX_SLOT_STATS; ++k) std::fprintf(fp, " %llu", rs[k]);
         std::fprintf(fp, "\n");
@@ -588,12 +644,12 @@ int run_batch(vx_ctx* c, const vx_frame_desc* frames, uint32_t nb) {
 
   float ms = 0;
   auto span = [&](int a, int b) {
-    cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]);
+    cudaEventElapsedTime(&ms, ln.ev[a], ln.ev[b]);
     return (double)ms;
   };
   for (uint32_t g = 0; g < n_sub; ++g) {
     auto sub = [&](int a, int b) {
-      cudaEventElapsedTime(&ms, c->ev_sub[4 * g + a], c->ev_sub[4 * g + b]);
+      cudaEventElapsedTime(&ms, ln.ev_sub[4 * g + a], ln.ev_sub[4 * g + b]);
       return (double)ms;
     };
     c->times.fill_ms += sub(0, 1);
@@ -628,53 +684,171 @@ void evict_locked(vx_ctx* c, uint32_t scan_id) {
   c->scans.erase(it);
 }
 
-// All frames of one call, in batches of equal size (a short last batch would leave most of the device idle for
-// a whole batch time).  Runs on the worker thread.
-int process_job(vx_ctx* c, const vx_frame_desc* frames, uint32_t n) {
-  VX_CUDA(c, cudaSetDevice(c->device));
-  const uint32_t n_batches = n ? (n + c->max_slots - 1) / c->max_slots : 0;
-  const uint32_t per_batch = n_batches ? (n + n_batches - 1) / n_batches : 0;
-  for (uint32_t base = 0; base < n;) {
-    uint32_t nb = n - base < per_batch ? n - base : per_batch;
-    if (nb > c->max_slots) nb = c->max_slots;
-    int rc = run_batch(c, frames + base, nb);
-    if (rc == VX_ERR_TABLE_OVERFLOW) {
-      // grow the histogram tables (x4) and redo this batch
-      if (c->log2_target >= 28) return fail(c, VX_ERR_TABLE_OVERFLOW, "histogram table overflow at 2^28 slots");
-      VX_CUDA(c, cudaStreamSynchronize(c->stream));
-      free_slots(c);
-      c->log2_target += 2;
-      c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
-      size_t free_b = 0, total_b = 0;
-      VX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-      while (c->table_sets > 1 && (size_t)c->table_sets * table_set_bytes(c) > free_b / 2) c->table_sets /= 2;
-      continue;
-    }
-    if (rc != VX_OK) return rc;
-    base += nb;
+// ---- the worker: jobs in submission order, their batches alternating between the lanes -------------------------------------
+
+Lane* oldest_busy(vx_ctx* c) {
+  Lane* best = nullptr;
+  for (uint32_t k = 0; k < 2; ++k)
+    if (c->lanes[k].busy && (!best || c->lanes[k].seq < best->seq)) best = &c->lanes[k];
+  return best;
+}
+
+// The batch on `ln` is over (rc = how): book it on its job; the job's last batch publishes the job.
+void settle_batch(vx_ctx* c, Lane& ln, int rc, const std::string& error) {
+  Job* job = ln.job;
+  if (rc != VX_OK && job->rc == VX_OK) {
+    job->rc = rc;
+    job->error = error;
   }
+  ln.busy = false;
+  ln.frames = nullptr;
+  ln.job = nullptr;
+  if (ln.owned) {
+    std::unique_ptr<Job> done = std::move(ln.owned);
+    {
+      std::lock_guard<std::mutex> lk(c->qmu);
+      if (done->rc != VX_OK) c->failed[done->ticket] = std::make_pair(done->rc, done->error);
+      c->finished_ticket = done->ticket;
+    }
+    c->dcv.notify_all();
+  }
+}
+
+int grow_tables(vx_ctx* c) {  // x4; every lane is idle
+  if (c->log2_target >= 28) return fail(c, VX_ERR_TABLE_OVERFLOW, "histogram table overflow at 2^28 slots");
+  for (uint32_t k = 0; k < 2; ++k)
+    if (c->lanes[k].stream) VX_CUDA(c, cudaStreamSynchronize(c->lanes[k].stream));
+  free_slots(c);
+  c->log2_target += 2;
+  c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
+  size_t free_b = 0, total_b = 0;
+  VX_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  while (c->table_sets > 1 && (size_t)c->table_sets * table_set_bytes(c) > free_b / 2) c->table_sets /= 2;
   return VX_OK;
+}
+
+// Completes the oldest batch in flight.  If its tables overflowed, the other lane is completed too (the tables are rebuilt), the
+// tables grow and the overflowed batches run again, one at a time; everything is settled oldest first.
+void retire_oldest(vx_ctx* c) {
+  Lane* ln = oldest_busy(c);
+  if (!ln) return;
+  std::string err;
+  tl_error_sink = &err;
+  int rc = finish_batch(c, *ln);
+  if (rc != VX_ERR_TABLE_OVERFLOW) {
+    tl_error_sink = nullptr;
+    settle_batch(c, *ln, rc, err);
+    return;
+  }
+  Lane* newer = nullptr;
+  for (uint32_t k = 0; k < 2; ++k)
+    if (c->lanes[k].busy && &c->lanes[k] != ln) newer = &c->lanes[k];
+  std::string err2;
+  int rc2 = VX_OK;
+  if (newer) {
+    tl_error_sink = &err2;
+    rc2 = finish_batch(c, *newer);
+  }
+  auto rerun = [&](Lane& l, std::string& e, bool grow_first) {
+    tl_error_sink = &e;
+    for (bool grow = grow_first;; grow = true) {
+      int r = grow ? grow_tables(c) : VX_OK;
+      if (r != VX_OK) return r;
+      l.busy = false;  // (enqueue_batch must not wait for this lane's own stale events)
+      Lane& o = &l == &c->lanes[0] ? c->lanes[1] : c->lanes[0];
+      const bool o_busy = o.busy;
+      o.busy = false;
+      r = enqueue_batch(c, l, o, l.frames, l.nb);
+      o.busy = o_busy;
+      l.busy = true;
+      if (r != VX_OK) return r;
+      r = finish_batch(c, l);
+      if (r != VX_ERR_TABLE_OVERFLOW) return r;
+    }
+  };
+  rc = rerun(*ln, err, true);
+  if (newer && (rc2 == VX_ERR_TABLE_OVERFLOW || rc2 == VX_OK)) {
+    // the frame records of the newer batch went with the old tables: run it again whatever it said
+    rc2 = rerun(*newer, err2, false);
+  }
+  tl_error_sink = nullptr;
+  settle_batch(c, *ln, rc, err);
+  if (newer) settle_batch(c, *newer, rc2, err2);
+}
+
+// Enqueues every batch of a job; its last batch stays in flight (the job is published when that batch is settled).
+void run_job(vx_ctx* c, std::unique_ptr<Job> job) {
+  Job* j = job.get();
+  const uint32_t n = (uint32_t)j->frames.size();
+  auto abandon = [&](int rc, const std::string& error) {  // nothing of this job is in flight any more: publish the failure in order
+    while (oldest_busy(c)) retire_oldest(c);
+    if (j->rc == VX_OK) {
+      j->rc = rc;
+      j->error = error;
+    }
+    {
+      std::lock_guard<std::mutex> lk(c->qmu);
+      if (j->rc != VX_OK) c->failed[j->ticket] = std::make_pair(j->rc, j->error);
+      c->finished_ticket = j->ticket;
+    }
+    c->dcv.notify_all();
+  };
+  if (cudaSetDevice(c->device) != cudaSuccess) return abandon(VX_ERR_CUDA, "cudaSetDevice failed");
+  if (n == 0) return abandon(VX_OK, "");
+  // batches of equal size (a short last batch would leave most of the device idle for a whole batch time)
+  const uint32_t n_batches = (n + c->lane_cap - 1) / c->lane_cap;
+  const uint32_t per_batch = (n + n_batches - 1) / n_batches;
+  for (uint32_t base = 0; base < n;) {
+    const uint32_t nb = n - base < per_batch ? n - base : per_batch;
+    Lane& ln = c->lanes[c->next_lane];
+    Lane& other = c->lanes[c->next_lane ^ 1u];
+    while (ln.busy) retire_oldest(c);
+    if (j->rc != VX_OK) return abandon(j->rc, j->error);  // an earlier batch of this job failed
+    std::string err;
+    tl_error_sink = &err;
+    const int rc = enqueue_batch(c, ln, other, j->frames.data() + base, nb);
+    tl_error_sink = nullptr;
+    if (rc != VX_OK) {
+      cudaStreamSynchronize(ln.stream);
+      return abandon(rc, err);
+    }
+    ln.job = j;
+    base += nb;
+    if (base >= n) ln.owned = std::move(job);
+    c->next_lane = (c->next_lane + 1u) % c->depth;
+  }
 }
 
 void worker_main(vx_ctx* c) {
   for (;;) {
     std::unique_ptr<Job> job;
+    Lane* oldest = oldest_busy(c);
     {
       std::unique_lock<std::mutex> lk(c->qmu);
-      c->qcv.wait(lk, [&] { return c->stop || !c->queue.empty(); });
-      if (c->queue.empty()) return;  // stop requested and nothing left to run
-      job = std::move(c->queue.front());
-      c->queue.pop_front();
+      if (!oldest) {
+        c->qcv.wait(lk, [&] { return c->stop || !c->queue.empty(); });
+      } else if (c->queue.empty()) {
+        // A batch is in flight and nothing is queued: do not block in the driver -- a job submitted meanwhile must be enqueued
+        // behind it at once (that is the overlap) -- but look at the batch's end event every 100 us.
+        if (cudaEventQuery(oldest->ev[EV_END]) != cudaSuccess) {
+          cudaGetLastError();
+          c->qcv.wait_for(lk, std::chrono::microseconds(100), [&] { return !c->queue.empty(); });
+        }
+      }
+      if (!c->queue.empty()) {
+        job = std::move(c->queue.front());
+        c->queue.pop_front();
+      } else if (!oldest) {
+        return;  // stop requested, nothing queued, nothing in flight
+      }
     }
-    tl_error_sink = &job->error;
-    job->rc = process_job(c, job->frames.data(), (uint32_t)job->frames.size());
-    tl_error_sink = nullptr;
-    {
-      std::lock_guard<std::mutex> lk(c->qmu);
-      if (job->rc != VX_OK) c->failed[job->ticket] = std::make_pair(job->rc, job->error);
-      c->finished_ticket = job->ticket;
+    if (job) {
+      run_job(c, std::move(job));
+    } else if (cudaEventQuery(oldest->ev[EV_END]) == cudaSuccess) {
+      retire_oldest(c);
+    } else {
+      cudaGetLastError();
     }
-    c->dcv.notify_all();
   }
 }
 
@@ -733,7 +907,10 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
     VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
-  for (int i = 0; i < EV_COUNT; ++i) VX_CREATE_CUDA(cudaEventCreate(&c->ev[i]));
+  c->lanes[0].stream = c->stream;
+  VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->lanes[1].stream, cudaStreamNonBlocking));
+  for (uint32_t k = 0; k < 2; ++k)
+    for (int i = 0; i < EV_COUNT; ++i) VX_CREATE_CUDA(cudaEventCreate(&c->lanes[k].ev[i]));
   VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
   VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
   VX_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_copy_out, cudaEventDisableTiming));
@@ -825,6 +1002,14 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   if (want < 1) want = 1;
   if (c->table_sets > want) c->table_sets = want;
   c->max_slots = want;
+  // Two batches in flight (the second lane takes the upper half of the slots) unless the tables are kept for debugging, the
+  // caller asked for tiny batches, or a scratch buffer per resident CTA (needed once CTAs of two launches share the SMs) does
+  // not fit next to everything else.
+  c->depth = 2;
+  if (c->keep_tables || want < 2u || (size_t)resident * scratch_bytes(c) > free_b / 4) c->depth = 1;
+  c->lane_cap = c->depth == 2 ? want / 2u : want;
+  c->lanes[0].slot_base = 0;
+  c->lanes[1].slot_base = c->lane_cap;
   VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_slots), (size_t)want * sizeof(VxSlot)));
   VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_counters), (size_t)want * kCounterWords * sizeof(uint32_t)));
   VX_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_counters), (size_t)want * kCounterWords * sizeof(uint32_t)));
@@ -845,6 +1030,7 @@ void vx_destroy(vx_ctx* c) {
   }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->lanes[1].stream) cudaStreamSynchronize(c->lanes[1].stream);
   if (c->copy_in) cudaStreamSynchronize(c->copy_in);
   free_slots(c);
   for (auto& kv : c->scans) {
@@ -861,15 +1047,19 @@ void vx_destroy(vx_ctx* c) {
   for (void* p : c->scratch_slabs) cudaFree(p);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_locks) cudaFree(c->d_locks);
-  for (cudaEvent_t e : c->ev_sub) cudaEventDestroy(e);
+  for (uint32_t k = 0; k < 2; ++k) {
+    Lane& ln = c->lanes[k];
+    for (cudaEvent_t e : ln.ev_sub) cudaEventDestroy(e);
+    for (int i = 0; i < EV_COUNT; ++i)
+      if (ln.ev[i]) cudaEventDestroy(ln.ev[i]);
+    if (ln.h_stage) cudaFreeHost(ln.h_stage);
+    if (ln.d_stage) cudaFree(ln.d_stage);
+  }
+  if (c->lanes[1].stream) cudaStreamDestroy(c->lanes[1].stream);
   if (c->d_slots) cudaFree(c->d_slots);
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->d_reject_bits) cudaFree(c->d_reject_bits);
-  if (c->h_stage) cudaFreeHost(c->h_stage);
-  if (c->d_stage) cudaFree(c->d_stage);
-  for (int i = 0; i < EV_COUNT; ++i)
-    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1042,6 +1232,7 @@ int vx_sync(vx_ctx* c) {
   VX_CUDA(c, cudaSetDevice(c->device));
   VX_CUDA(c, cudaStreamSynchronize(c->copy_in));
   VX_CUDA(c, cudaStreamSynchronize(c->stream));
+  VX_CUDA(c, cudaStreamSynchronize(c->lanes[1].stream));
   std::lock_guard<std::mutex> lk(c->mu);
   prune_marks(c);
   return rc;
@@ -1068,7 +1259,7 @@ int vx_trace_ray(vx_ctx* c, uint32_t frame_index, int32_t i, int32_t j, int32_t 
   const size_t words = 2 + (size_t)visited_capacity * 3;
   VX_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&d_buf), words * 4));
   std::vector<int32_t> host(words);
-  cudaError_t e = vx_launch_trace_ray(c->slots[frame_index].dev.occ, c->geom, i, j, k, endpoint, d_buf + 2, visited_capacity, d_buf, c->stream);
+  cudaError_t e = vx_launch_trace_ray(c->slots[c->last_base + frame_index].dev.occ, c->geom, i, j, k, endpoint, d_buf + 2, visited_capacity, d_buf, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), d_buf, words * 4, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(d_buf);
@@ -1085,7 +1276,7 @@ int vx_debug_dump(vx_ctx* c, uint32_t frame_index, int kind, void* dst, uint64_t
   if (!c || !count) return fail(c, VX_ERR_INVALID, "null argument");
   if (frame_index >= c->last_batch) return fail(c, VX_ERR_INVALID, "frame index outside the last batch");
   VX_CUDA(c, cudaSetDevice(c->device));
-  const VxSlot& s = c->slots[frame_index].dev;
+  const VxSlot& s = c->slots[c->last_base + frame_index].dev;
   if (kind == VX_DUMP_HIST_TARGET || kind == VX_DUMP_HIST_INPUT) {
     if (!c->keep_tables || !c->tables_dirty) return fail(c, VX_ERR_INVALID, "histogram dump needs vx_options.debug = 1");
     const VxTable& t = kind == VX_DUMP_HIST_TARGET ? s.target : s.input;
