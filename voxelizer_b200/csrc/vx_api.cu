@@ -120,7 +120,7 @@ struct vx_ctx {
   std::unordered_map<uint32_t, DeviceScan> scans;
   cudaMemPool_t scan_pool = nullptr;  // private stream-ordered pool of the scan cache
 
-  uint32_t max_slots = 0;   // frames per batch (one visibility launch)
+  uint32_t max_slots = 0;   // frame records: depth x lane_cap (a lane holds one batch = one visibility launch)
   uint32_t table_sets = 0;  // frames per fill -> vote -> emit launch
   uint32_t log2_target = 18, log2_input = 15;
   bool occlusion_labels = false;  // vx_options.occlusion_labels: slots and scratch carry the arrays insertOcclusionLabels needs
@@ -988,31 +988,30 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   uint32_t want = options && options->frames_in_flight ? options->frames_in_flight : 4u * resident;
   if (c->keep_tables && want > 8u && !(options && options->frames_in_flight)) want = 8u;  // debug: small batches,
   if (c->keep_tables || want < c->table_sets) c->table_sets = want;                       // every frame its own tables
+  // Two batches in flight (two lanes, each with frame records for a whole batch) unless the tables are kept for debugging or a
+  // scratch buffer per resident CTA (needed once CTAs of two launches share the SMs) does not fit next to everything else.
+  c->depth = 2;
+  if (c->keep_tables || (size_t)resident * scratch_bytes(c) > free_b / 4) c->depth = 1;
   {  // the largest batch whose frame records, histogram tables and traversal scratch fit into 70 % of the free memory
-     // (scratch: one buffer per RESIDENT CTA, at most one per frame; tables: one set per frame of a fill group)
+     // (scratch: one buffer per RESIDENT CTA -- at most one per frame with one lane; tables: one set per frame of a fill group)
     const size_t budget = free_b / 10 * 7;
     auto cost = [&](uint32_t n) {
-      const size_t n_scratch = n < resident ? n : resident;
+      const size_t n_scratch = (c->depth == 1 && n < resident) ? n : resident;
       const size_t n_sets = n < c->table_sets ? n : c->table_sets;
-      return n_scratch * scratch_bytes(c) + n_sets * table_set_bytes(c) + (size_t)n * frame_bytes(c);
+      return n_scratch * scratch_bytes(c) + n_sets * table_set_bytes(c) + (size_t)c->depth * n * frame_bytes(c);
     };
     while (want > 1 && cost(want) > budget) want = want - (want + 3) / 4;
   }
-  if (want > 65535u) want = 65535u;
+  if (want > 32767u) want = 32767u;
   if (want < 1) want = 1;
   if (c->table_sets > want) c->table_sets = want;
-  c->max_slots = want;
-  // Two batches in flight (the second lane takes the upper half of the slots) unless the tables are kept for debugging, the
-  // caller asked for tiny batches, or a scratch buffer per resident CTA (needed once CTAs of two launches share the SMs) does
-  // not fit next to everything else.
-  c->depth = 2;
-  if (c->keep_tables || want < 2u || (size_t)resident * scratch_bytes(c) > free_b / 4) c->depth = 1;
-  c->lane_cap = c->depth == 2 ? want / 2u : want;
+  c->lane_cap = want;                 // frames per batch
+  c->max_slots = c->depth * want;     // frame records (allocated as batches need them)
   c->lanes[0].slot_base = 0;
   c->lanes[1].slot_base = c->lane_cap;
-  VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_slots), (size_t)want * sizeof(VxSlot)));
-  VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_counters), (size_t)want * kCounterWords * sizeof(uint32_t)));
-  VX_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_counters), (size_t)want * kCounterWords * sizeof(uint32_t)));
+  VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_slots), (size_t)c->max_slots * sizeof(VxSlot)));
+  VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_counters), (size_t)c->max_slots * kCounterWords * sizeof(uint32_t)));
+  VX_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_counters), (size_t)c->max_slots * kCounterWords * sizeof(uint32_t)));
 #undef VX_CREATE_CUDA
   *out = c;
   return VX_OK;
@@ -1079,7 +1078,7 @@ int vx_grid_info_get(const vx_ctx* c, vx_grid_info* out) {
   return VX_OK;
 }
 
-uint32_t vx_frames_in_flight(const vx_ctx* c) { return c ? c->max_slots : 0; }
+uint32_t vx_frames_in_flight(const vx_ctx* c) { return c ? c->lane_cap : 0; }
 
 int vx_upload_scan(vx_ctx* c, uint32_t scan_id, const float* xyzr, const uint32_t* labels, uint32_t n) {
   if (!c || (n && (!xyzr || !labels))) return fail(c, VX_ERR_INVALID, "null argument");
