@@ -146,6 +146,7 @@ struct vx_ctx {
   std::vector<cudaEvent_t> ev_pool;   // timing-less events
 
   Lane lanes[2];            // lanes[0].stream == stream
+  bool leave_room = false;  // see vx_launch_visibility
   uint32_t depth = 1;       // batches in flight at a time (2 unless the tables are kept for debugging or memory is short)
   uint32_t lane_cap = 0;    // frames per batch
   uint32_t next_lane = 0;
@@ -543,8 +544,17 @@ int enqueue_batch(vx_ctx* c, Lane& ln, Lane& other, const vx_frame_desc* frames,
   // ONE visibility launch per batch.  (Measured: a launch per group on streams of their own, started as soon as the
   // group is filled, is slower -- every launch places its CTAs on the SMs in the same order, so 8 launches of 114
   // CTAs load 114 SMs with 7 CTAs and leave 34 idle; with groups of 148 it still lost 6 % to the single launch.)
+  int leave_room = 0;  // VX_B200_LEAVE_ROOM=1 (developer switch, A/B): 6 traversal CTAs per SM while another batch is in flight / queued
+  if (c->leave_room && c->depth == 2) {
+    bool queued = false;
+    {
+      std::lock_guard<std::mutex> qk(c->qmu);
+      queued = !c->queue.empty();
+    }
+    leave_room = (other.busy || queued) ? 1 : 0;
+  }
   VX_CUDA(c, cudaEventRecord(ln.ev[EV_VIS_BEGIN], st));
-  VX_CUDA(c, vx_launch_visibility(c->d_slots + base, d_vis, nb, d_ep, c->geom, c->d_scratch, n_scratch, c->d_locks, c->vis_mode, st));
+  VX_CUDA(c, vx_launch_visibility(c->d_slots + base, d_vis, nb, d_ep, c->geom, c->d_scratch, n_scratch, c->d_locks, c->vis_mode, leave_room, st));
   VX_CUDA(c, cudaEventRecord(ln.ev[EV_VIS], st));
   VX_CUDA(c, vx_launch_pack(c->d_slots + base, nb, c->nvox, st));
   VX_CUDA(c, cudaEventRecord(ln.ev[EV_PACK], st));
@@ -990,6 +1000,7 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   if (c->keep_tables || want < c->table_sets) c->table_sets = want;                       // every frame its own tables
   // Two batches in flight (two lanes, each with frame records for a whole batch) unless the tables are kept for debugging or a
   // scratch buffer per resident CTA (needed once CTAs of two launches share the SMs) does not fit next to everything else.
+  if (const char* e = std::getenv("VX_B200_LEAVE_ROOM")) c->leave_room = std::atoi(e) != 0;
   c->depth = 2;
   if (c->keep_tables || (size_t)resident * scratch_bytes(c) > free_b / 4) c->depth = 1;
   {  // the largest batch whose frame records, histogram tables and traversal scratch fit into 70 % of the free memory

@@ -99,14 +99,52 @@ vx_fill_kernel(const VxScanWork* __restrict__ works, const VxScanUse* __restrict
   uint32_t keep0 = 0;
   {
     float4 p[kFillPointsPerThread];
+#ifdef VX_FILL_TMA
+    // A/B (tools/build_variants.py ...,VX_FILL_TMA=1): the tile staged in shared memory by ONE bulk copy per array (cp.async.bulk +
+    // mbarrier, the 1-D TMA path; SASS UBLKCP) instead of one ld.global.cs per point and thread.  Full tiles only (16-byte sizes).
+    __shared__ __align__(128) float4 tile_points[kFillTile];
+    __shared__ __align__(16) uint32_t tile_labels[kFillTile];
+    __shared__ __align__(8) unsigned long long tile_bar;
+    const bool bulk = base + kFillTile <= w.n;
+    if (bulk) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tile_bar);
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const uint32_t bytes_p = kFillTile * 16u, bytes_l = kFillTile * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_p + bytes_l) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(tile_points)), "l"(w.points + base), "r"(bytes_p), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(tile_labels)), "l"(w.labels + base), "r"(bytes_l), "r"(bar) : "memory");
+      }
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+      }
+    }
+#else
+    constexpr bool bulk = false;
+#endif
 #pragma unroll
     for (int u = 0; u < kFillPointsPerThread; ++u) {
       const uint32_t idx = base + u * kFillThreads + threadIdx.x;
       p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       lab[u] = 0;
       if (idx < w.n) {
-        p[u] = __ldcs(w.points + idx);  // a scan is streamed once per launch: evict-first
-        lab[u] = __ldcs(w.labels + idx) & 0xFFFFu;
+#ifdef VX_FILL_TMA
+        if (bulk) {
+          p[u] = tile_points[u * kFillThreads + threadIdx.x];
+          lab[u] = tile_labels[u * kFillThreads + threadIdx.x] & 0xFFFFu;
+        } else
+#endif
+        {
+          p[u] = __ldcs(w.points + idx);  // a scan is streamed once per launch: evict-first
+          lab[u] = __ldcs(w.labels + idx) & 0xFFFFu;
+        }
         keep0 |= 1u << u;
       }
     }

@@ -24,7 +24,7 @@ cudaError_t vx_visibility_prepare();  // opt-in to large dynamic shared memory (
 int vx_visibility_resident_ctas(int device);  // CTAs of the kernel the device holds at once
 cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, uint32_t n_slots,
                                  const float* endpoints, VxGridGeom geom, const VxVisScratch* scratch, uint32_t n_scratch,
-                                 uint32_t* locks, int mode, cudaStream_t stream);
+                                 uint32_t* locks, int mode, int leave_room, cudaStream_t stream);
 uint64_t vx_visibility_visits(VxGridGeom geom);  // visits per pass (must stay < 2^25)
 
 // VoxelGrid::occludedBy as a public call: one ray over a frame's occupancy; visited = capacity x (i, j, k), result = {cells

@@ -37,6 +37,7 @@
 // bitmap of 4x4x1-voxel blocks (5 % of the steps need the exact bit from global memory); leaving the
 // grid is one zero-field test on the packed position (trace_warp).  Global traffic: one memo read per live visit,
 // one fire-and-forget RED per ray step, one hit-bit gather per live visit.
+#include <algorithm>
 #include <cstdio>
 #include <type_traits>
 
@@ -1108,9 +1109,11 @@ cudaError_t vx_launch_trace_ray(const uint32_t* occ, VxGridGeom geom, int32_t i,
 using CfgThroughput = VisCfg<VX_THR_THREADS, VX_THR_MAXLIVE, 256, VX_THR_CTAS, VX_THR_COARSE>;
 using CfgLatency = VisCfg<512, 8192, 1024, 1>;
 
+constexpr size_t kRoomySmem = 36 * 1024;  // 6 x (36 + 1) KB fit an SM, 7 do not
+
 cudaError_t vx_visibility_prepare() {
   cudaError_t e = cudaFuncSetAttribute(vx_visibility_kernel<CfgThroughput>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(VisShared<CfgThroughput>));
+                                       (int)std::max(sizeof(VisShared<CfgThroughput>), kRoomySmem));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(vx_visibility_kernel<CfgLatency>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisShared<CfgLatency>));
 }
@@ -1126,10 +1129,13 @@ int vx_visibility_resident_ctas(int device) {
   return (a > b ? a : b) * sms;
 }
 
-// mode: 0 = by batch size (latency shape when the frames cannot even give every SM two CTAs), 1 = throughput, 2 = latency
+// mode: 0 = by batch size (latency shape when the frames cannot even give every SM two CTAs), 1 = throughput, 2 = latency.
+// leave_room: another batch is in flight or queued -- the throughput shape then asks for a little more shared memory than it uses,
+// so that an SM holds 6 instead of 7 of its CTAs and keeps registers for one CTA of the other batch's fill / vote / emit kernels
+// (which otherwise crawl behind ~900 resident traversal CTAs: 294 / 175 / 478 ms instead of 40 / 3 / 6 per step).
 cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, uint32_t n_slots,
                                  const float* endpoints, VxGridGeom geom, const VxVisScratch* scratch, uint32_t n_scratch,
-                                 uint32_t* locks, int mode, cudaStream_t stream) {
+                                 uint32_t* locks, int mode, int leave_room, cudaStream_t stream) {
   if (n_slots == 0) return cudaSuccess;
   const uint32_t hit_words = (uint32_t)(vx_visibility_visits(geom) / 32u + 1u);
   if (mode == 0) {
@@ -1140,9 +1146,12 @@ cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, 
   if (mode == 2)
     vx_visibility_kernel<CfgLatency><<<n_slots, CfgLatency::kThreads, sizeof(VisShared<CfgLatency>), stream>>>(
         slots, frames, endpoints, geom, hit_words, scratch, n_scratch, locks);
-  else
-    vx_visibility_kernel<CfgThroughput><<<n_slots, CfgThroughput::kThreads, sizeof(VisShared<CfgThroughput>), stream>>>(
+  else {
+    size_t smem = sizeof(VisShared<CfgThroughput>);
+    if (leave_room && smem < kRoomySmem) smem = kRoomySmem;
+    vx_visibility_kernel<CfgThroughput><<<n_slots, CfgThroughput::kThreads, smem, stream>>>(
         slots, frames, endpoints, geom, hit_words, scratch, n_scratch, locks);
+  }
   return cudaGetLastError();
 }
 
