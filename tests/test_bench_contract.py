@@ -34,7 +34,7 @@ def test_reference_arm_other_ranks_exit_without_work():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-@pytest.mark.parametrize("name", ["r01_bench_n1.json", "r01_bench_n2.json", "r01_bench_n8.json"])
+@pytest.mark.parametrize("name", ["r01_bench_n1.json", "r01_bench_n2.json", "r01_bench_n8.json", "r02_bench_n1.json", "r02_bench_n2.json"])
 def test_committed_bench_lines_have_the_contract_keys(name):
     path = os.path.join(ROOT, "profiles", name)
     d = json.loads(open(path).read().strip().splitlines()[-1])
@@ -49,3 +49,20 @@ def test_committed_bench_lines_have_the_contract_keys(name):
     if d["n_gpus"] == 1:
         c = d["cpu_baseline"]
         assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+
+
+def test_round2_lines_carry_the_parity_check_and_the_extra_records():
+    n1 = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")).read().strip().splitlines()[-1])
+    pc = n1["parity_check"]
+    assert pc["oracle"] == "ref" and pc["mismatches"] == 0 and pc["files"] == 4 * pc["frames"] >= 16
+    assert n1["single_step"]["value"] > 0 and n1["single_step"]["value"] <= n1["value"] * 1.05
+    assert set(n1["extra_configs"]) == {"dense", "stress_512", "past1000"}
+    for rec in n1["extra_configs"].values():
+        assert rec["value"] > 0 and rec["frames"] > 0 and "reference" in rec
+    assert n1["cpu_baseline"]["single_thread"]["cores"] == 1
+    assert "profiles/r02_fill_traffic.json" in n1["roofline"]["traffic_source"]
+    n2 = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_n2.json")).read().strip().splitlines()[-1])
+    for rec in n2["strong"].values():
+        assert rec["files_equal"] is True and rec["speedup"] > 1.0 and rec["n_gpus"] == 2
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_reference_arm.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["cpu_baseline"]["kind"] == "reference" and len(ref["frame_hashes"]) == ref["config"]["frames_per_step"]

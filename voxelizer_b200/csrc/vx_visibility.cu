@@ -928,7 +928,9 @@ vx_visibility_kernel(const VxSlot* __restrict__ slots, const VxVisFrame* __restr
     }
     build_axis_table(f, sm);  // (barrier inside)
     if (pass % kMaxEpoch == 0) {  // first pass, or the epoch counter restarts: forget every memo
-      for (uint32_t x = tid; x < nvox; x += C::kThreads) f.memo[x] = 0u;
+      uint4* const memo4 = reinterpret_cast<uint4*>(f.memo);  // (the scratch arenas are 256-byte aligned)
+      for (uint32_t x = tid; x < (nvox >> 2); x += C::kThreads) memo4[x] = make_uint4(0u, 0u, 0u, 0u);
+      for (uint32_t x = (nvox & ~3u) + tid; x < nvox; x += C::kThreads) f.memo[x] = 0u;
     }
     __syncthreads();
 
