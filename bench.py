@@ -517,10 +517,11 @@ def run_ours(args):
     if ring is not None:
         outs = output_views(ring, be, n_frames)
         ring_b = None
-        try:
-            ring_b = vx.PinnedBuffer(n_frames * per)   # a second output ring: two steps are in flight
-        except Exception:
-            ring_b = None
+        if int(os.environ.get("VX_BENCH_E2E_DEPTH", "1")) == 2:
+            try:
+                ring_b = vx.PinnedBuffer(n_frames * per)   # a second output ring: two steps in flight
+            except Exception:
+                ring_b = None
         if world > 1:
             ok = torch.tensor([1 if ring_b is not None else 0], dtype=torch.int32, device="cuda")
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)

@@ -1109,7 +1109,10 @@ cudaError_t vx_launch_trace_ray(const uint32_t* occ, VxGridGeom geom, int32_t i,
 #define VX_THR_COARSE 4096
 #endif
 using CfgThroughput = VisCfg<VX_THR_THREADS, VX_THR_MAXLIVE, 256, VX_THR_CTAS, VX_THR_COARSE>;
-using CfgLatency = VisCfg<512, 8192, 1024, 1>;
+#ifndef VX_LAT_THREADS
+#define VX_LAT_THREADS 512
+#endif
+using CfgLatency = VisCfg<VX_LAT_THREADS, 8192, 1024, 1>;
 
 constexpr size_t kRoomySmem = 36 * 1024;  // 6 x (36 + 1) KB fit an SM, 7 do not
 
