@@ -767,11 +767,25 @@ def run_strong(vx, torch, dist, args, rank, world, device, host_threads, seq0, r
         total = len(targets)
         lo, hi = total * rank // world, total * (rank + 1) // world      # gen_data_pipeline.cpp's --shard i/n split
         mine = targets[lo:hi]
-        be = vx.Backend.from_config(cfg, device=device, stream=stream, frames_in_flight=min(total, 1036))
+        # (a call is one batch = one traversal launch of up to 2271 CTAs: those beyond the ~1036 resident ones start as frames finish)
+        be = vx.Backend.from_config(cfg, device=device, stream=stream, frames_in_flight=min(total, 2271))
         per_c = be.label_bytes + 3 * be.packed_bytes
-        chunk = max(1, min(len(mine) if len(mine) else 1, ring.nbytes // per_c)) if ring is not None else 0
-        if ring is None or chunk == 0:
-            result[name] = {"skipped": "no pinned output ring"}
+        # Output ring of this leg: as many frames as one call should hold (up to 2271 = half the dense job: 10.8 GB pinned).  Rank 0's
+        # single-GPU run uses the same size whatever N is, so the baseline of `speedup` does not depend on the number of ranks.
+        big_frames = min(total, 2271) if rank == 0 else max(1, min(len(mine), 2271))
+        big = None
+        try:
+            big = vx.PinnedBuffer(big_frames * per_c)
+        except Exception as exc:
+            sys.stderr.write(f"bench: rank {rank}: no {big_frames}-frame output ring for the strong leg ({exc}); using the e2e ring\n")
+        ring_s = big if big is not None else ring
+        ok = torch.tensor([1 if ring_s is not None else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            if rank == 0:
+                result[name] = {"skipped": "no pinned output ring"}
+            if big is not None:
+                big.free()
             be.close()
             continue
 
@@ -784,12 +798,12 @@ def run_strong(vx, torch, dist, args, rank, world, device, host_threads, seq0, r
             else:
                 s, own = Sequence(vx, 1234, first, last - first, host_threads), True
             specs, kept, _ = plan_frames(vx, cfg, n_scans, poses, s, targets=tg)
-            warm_up(vx, backend, s, specs, ring, first)
+            warm_up(vx, backend, s, specs, ring_s, first)
             dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             s.upload(backend, first, last)                               # pinned host -> HBM: part of the timed job
-            busy, digests = run_host_job(vx, backend, s, specs, ring, max(1, min(len(specs), ring.nbytes // per_c)))
+            busy, digests = run_host_job(vx, backend, s, specs, ring_s, max(1, min(len(specs), ring_s.nbytes // per_c)))
             backend.sync()
             wall = time.perf_counter() - t0
             backend.evict_all()
@@ -806,7 +820,7 @@ def run_strong(vx, torch, dist, args, rank, world, device, host_threads, seq0, r
         dist.all_gather_object(gathered, (kept, [d.hex() for d in digests], scans_read))
         rec = None
         if rank == 0:
-            busy1, wall1, digests1, kept1, _ = shard_job_single(vx, be, cfg, n_scans, poses, targets, ring, per_c, seq0 if name == "dense" else None,
+            busy1, wall1, digests1, kept1, _ = shard_job_single(vx, be, cfg, n_scans, poses, targets, ring_s, per_c, seq0 if name == "dense" else None,
                                                                host_threads)
             sharded = {}
             for kept_r, dig_r, _ in gathered:
@@ -822,7 +836,10 @@ def run_strong(vx, torch, dist, args, rank, world, device, host_threads, seq0, r
                              "copies into pinned host memory included; hashing excluded); the single-GPU run is timed the same way on rank 0"}
         dist.barrier()
         be.close()
+        if big is not None:
+            big.free()
         if rank == 0:
+            rec["frames_per_call"] = big_frames if big is not None else ring.nbytes // per_c
             result[name] = rec
     return result if rank == 0 else None
 
