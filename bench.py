@@ -470,12 +470,14 @@ def run_ours(args):
     # the finished frames leave.  `single_step` below is the same job with a wait after every step.
     seq.upload(be)
 
+    lanes = max(1, be.batches_in_flight)
+
     def run_steps(k):
         tickets = []
         for _ in range(k):
             tickets.append(be.submit_descs(descs_dev, n_frames))
-            if len(tickets) > 2:
-                be.wait(tickets[-3])
+            if len(tickets) > lanes:             # one job queued behind the batches in flight
+                be.wait(tickets[-(lanes + 1)])
         be.wait(0)
 
     step_dev = lambda: be.process_descs(descs_dev, n_frames)
@@ -495,7 +497,9 @@ def run_ours(args):
         total_frames = int(tf)
     value = total_frames / (ms_per_step / 1e3)
     n_single = min(3, args.steps)
+    be.reset_stage_times()
     s_dev_ms, _ = timed(step_dev, n_single)
+    st_single = be.stage_times()                 # every kernel of these steps ran with the device to itself
     single_step = {"value": total_frames / (s_dev_ms / n_single / 1e3), "unit": UNIT, "ms_per_step": s_dev_ms / n_single, "steps": n_single,
                    "what": "the same step with a wait after each one (vx_process_frames): bound by the slowest frame of a 909-frame batch"}
 
@@ -515,55 +519,47 @@ def run_ours(args):
             if int(ok) == 0:
                 ring = None
     if ring is not None:
-        outs = output_views(ring, be, n_frames)
-        ring_b = None
-        if int(os.environ.get("VX_BENCH_E2E_DEPTH", "1")) == 2:
+        # Steps in flight = the library's lanes (VX_BENCH_E2E_DEPTH overrides): every step in flight has its own scan id range in
+        # HBM and its own pinned output ring, so nothing a step reads or writes is touched before the step has been awaited.
+        depth = max(1, min(4, int(os.environ.get("VX_BENCH_E2E_DEPTH", str(lanes)))))
+        rings = [ring]
+        while len(rings) < depth:
             try:
-                ring_b = vx.PinnedBuffer(n_frames * per)   # a second output ring: two steps in flight
+                rings.append(vx.PinnedBuffer(n_frames * per))
             except Exception:
-                ring_b = None
+                break
         if world > 1:
-            ok = torch.tensor([1 if ring_b is not None else 0], dtype=torch.int32, device="cuda")
+            ok = torch.tensor([len(rings)], dtype=torch.int32, device="cuda")
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok) == 0 and ring_b is not None:
-                ring_b.free()
-                ring_b = None
-        outs_b = output_views(ring_b, be, n_frames) if ring_b is not None else outs
-        ID2 = 1 << 20  # second id range
+            while len(rings) > int(ok):
+                rings.pop().free()
+        depth = len(rings)
+        outs_of = [output_views(r, be, n_frames) for r in rings]
+        offsets = [r << 20 for r in range(depth)]  # scan id ranges
         sets = []
-        for off, o in ((0, outs), (ID2, outs_b)):
+        for off, o in zip(offsets, outs_of):
             sp = [vx.FrameSpec(s.prior_ids + off, s.ap_prior, s.past_ids + off, s.ap_past, s.endpoints) for s in specs] if off else specs
             sets.append(be.build_descs(sp, o))
-        offsets = (0, ID2)
-        # steps in flight: 1 = the next step's scans cross PCIe while this step is traversed, then the step is awaited (the
-        # measured optimum: with two steps in flight the next step's fill kernels starve behind 909 resident traversal CTAs)
-        depth = int(os.environ.get("VX_BENCH_E2E_DEPTH", "1"))
-        if ring_b is None:
-            depth = 1
 
         def evict_set(off):
             for t in range(n_scans):
                 be.evict_scan(t + off)
 
         def run_e2e(k_steps):
-            """k steps, each: its scans from pinned host memory into HBM under one of two id ranges, vx_submit_frames with host
-            output buffers, at most `depth` steps in flight; returns when every output of every step has landed."""
+            """k steps, each: its scans from pinned host memory into HBM under one of `depth` id ranges, vx_submit_frames with host
+            output buffers (its own ring), at most `depth` steps in flight; returns when every output of every step has landed."""
             tickets = []
-            evict_set(offsets[0])
-            seq.upload(be, id_offset=offsets[0])
             for k in range(k_steps):
-                tickets.append(be.submit_descs(sets[k % 2][0], n_frames))
-                if depth == 2 and k >= 1:
-                    be.wait(tickets[k - 1])          # the other id range (and ring) is free again
-                if k + 1 < k_steps:                  # the next step's inputs cross PCIe while this step runs
-                    evict_set(offsets[(k + 1) % 2])
-                    seq.upload(be, id_offset=offsets[(k + 1) % 2])
-                if depth == 1:
-                    be.wait(tickets[k])
+                r = k % depth
+                if k >= depth:
+                    be.wait(tickets[k - depth])      # id range and ring r are free again
+                evict_set(offsets[r])
+                seq.upload(be, id_offset=offsets[r])  # crosses PCIe while the steps in flight are traversed
+                tickets.append(be.submit_descs(sets[r][0], n_frames))
             be.wait(0)
 
         be.evict_all()
-        run_e2e(2)                                  # warm-up
+        run_e2e(max(2, depth))                      # warm-up (every id range and ring once)
         e_dev_ms, e_wall_ms = timed(lambda: run_e2e(max(1, args.steps)), 1)
         be.sync()
         e_ms = e_wall_ms / max(1, args.steps)       # wall clock: includes every host-side gap
@@ -572,9 +568,8 @@ def run_ours(args):
         e2e = {"value": total_frames / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                "ms_per_step": e_ms, "device_ms_per_step": e_dev_ms / max(1, args.steps), "steps_in_flight": depth,
                "how": "every step uploads all its scans from pinned host memory and gets all four images of every frame back in pinned host "
-                      "memory; steps are submitted with vx_submit_frames, two in flight (two scan id ranges, two output rings)"}
-        last = (max(1, args.steps) - 1) % 2
-        outs = outs if last == 0 else outs_b         # the step that finished last
+                      f"memory; steps are submitted with vx_submit_frames, {depth} in flight (a scan id range and an output ring each)"}
+        outs = outs_of[(max(1, args.steps) - 1) % depth]   # the step that finished last
         # ---- parity of the benchmarked workload: the frames the reference arm computed, byte for byte
         if ref_line and ref_line.get("frame_hashes"):
             index = {t: i for i, t in enumerate(spec_targets)}
@@ -596,8 +591,8 @@ def run_ours(args):
                 parity_check["first_bad"] = bad[:8]
         be.evict_all()
         seq.upload(be)                          # back to the plain id range for what follows
-        if ring_b is not None:
-            ring_b.free()
+        for r in rings[1:]:
+            r.free()
 
     # ---- optional legs, outside the headline's timed regions
     extra_configs, strong = None, None
@@ -612,11 +607,19 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         nvox = be.nvox
         launches = {k: int(st[k]) for k in ("fill_launches", "vote_launches", "emit_launches", "visibility_launches", "pack_launches")}
-        fill_bytes = 20.0 * st["points_read"]                                   # xyzr 16 B + label 4 B per window point
-        fill_s = st["fill_ms"] / 1e3
-        fill_gbs = fill_bytes / fill_s / 1e9 if fill_s > 0 else 0.0
-        ivp_bytes = fill_bytes + st["frames"] * (2.0 * nvox + 3.0 * nvox / 8.0)  # SURVEY.md 8(d) B_frame
-        ivp_s = (st["fill_ms"] + st["vote_ms"] + st["emit_ms"] + st["pack_ms"]) / 1e3
+        # Roofline of the dominant HBM-side kernel, from the `single_step` leg: there every kernel has the device to itself, which
+        # is what a roofline fraction is about.  In the back-to-back leg the fill kernels of batch k + 2 run (on purpose, and off
+        # the critical path) in the few registers that ~1000 resident traversal CTAs leave: `overlapped` states that figure too.
+        def hbm_side(t):
+            fb = 20.0 * t["points_read"]                                        # xyzr 16 B + label 4 B per window point
+            fs_ = t["fill_ms"] / 1e3
+            ib = fb + t["frames"] * (2.0 * nvox + 3.0 * nvox / 8.0)             # SURVEY.md 8(d) B_frame
+            is_ = (t["fill_ms"] + t["vote_ms"] + t["emit_ms"] + t["pack_ms"]) / 1e3
+            return fb, (fb / fs_ / 1e9 if fs_ > 0 else 0.0), ib, (ib / is_ / 1e9 if is_ > 0 else 0.0)
+
+        fill_bytes, fill_gbs, ivp_bytes, ivp_gbs = hbm_side(st_single)
+        fill_launches_single = max(1, int(st_single["fill_launches"]))
+        _, ov_fill_gbs, _, ov_ivp_gbs = hbm_side(st)
         traffic = fill_traffic_factor()
         vis_s = st["visibility_ms"] / 1e3
         line = {
@@ -628,7 +631,7 @@ def run_ours(args):
                        "frames_per_step_per_gpu": n_frames, "frames_in_flight": be.frames_in_flight,
                        "l2_policy": "inputs larger than L2 (window of one frame = 180 MB, sequence = 11.6 GB)",
                        "parallelism": f"{world} x independent target-range shards, no data-path collective",
-                       "steps": "submitted back to back, two batches in flight (stage_ms_per_step sums overlapping kernels)"},
+                       "steps": f"submitted back to back, {lanes} batches in flight (stage_ms_per_step sums overlapping kernels)"},
             "wall_ms_per_step": wall_ms / args.steps,
             "single_step": single_step,
             "gpu_launches": sum(launches.values()),
@@ -638,15 +641,19 @@ def run_ours(args):
                          "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak,
                          # DRAM bytes per launch are NOT measured by this run: they are the algorithmic bytes of this run's launches
                          # times the dram/algorithmic ratio of the tracked ncu capture named in traffic_source
-                         "traffic": traffic["factor"] * fill_bytes / max(1, launches["fill_launches"]) if traffic["factor"] else None,
+                         "traffic": traffic["factor"] * fill_bytes / fill_launches_single if traffic["factor"] else None,
                          "traffic_source": traffic["source"],
-                         "peak_source": peak_src, "bytes_per_launch": fill_bytes / max(1, launches["fill_launches"]),
+                         "peak_source": peak_src, "bytes_per_launch": fill_bytes / fill_launches_single,
                          # algorithmic bytes of each fill launch of one step, in launch order (one launch per 128 frames)
                          "bytes_of_launch": [20 * sum(spec_points[a:a + 128]) for a in range(0, n_frames, 128)],
-                         "ms_per_launch": st["fill_ms"] / max(1, launches["fill_launches"]),
-                         "insert_vote_pack": {"achieved": ivp_bytes / ivp_s / 1e9 if ivp_s > 0 else 0.0,
-                                              "frac": (ivp_bytes / ivp_s / 1e9 / peak) if ivp_s > 0 else 0.0,
-                                              "bytes_per_frame": ivp_bytes / max(1, st["frames"])}},
+                         "ms_per_launch": st_single["fill_ms"] / fill_launches_single,
+                         "timed_in": f"the single_step leg ({n_single} steps, CUDA events around every launch on its own stream): "
+                                     "the kernel has the device to itself",
+                         "insert_vote_pack": {"achieved": ivp_gbs, "frac": ivp_gbs / peak,
+                                              "bytes_per_frame": ivp_bytes / max(1, st_single["frames"])},
+                         "overlapped": {"achieved": ov_fill_gbs, "frac": ov_fill_gbs / peak, "insert_vote_pack_frac": ov_ivp_gbs / peak,
+                                        "what": "the same kernels in the back-to-back leg (`value`), where they share the SMs with the "
+                                                "resident traversal CTAs of the batches ahead and are off the critical path"}},
             "traversal": {"kernel": "vx_visibility_kernel (K4)", "rays_per_frame": st["rays_cast"] / max(1, st["frames"]),
                           "dda_steps_per_frame": st["dda_steps"] / max(1, st["frames"]),
                           "gsteps_per_s": st["dda_steps"] / vis_s / 1e9 if vis_s > 0 else 0.0,

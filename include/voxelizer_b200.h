@@ -156,6 +156,8 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
 void vx_destroy(vx_ctx* ctx);
 int vx_grid_info_get(const vx_ctx* ctx, vx_grid_info* out);
 uint32_t vx_frames_in_flight(const vx_ctx* ctx); /* frames one internal batch holds */
+uint32_t vx_batches_in_flight(const vx_ctx* ctx); /* batches the library keeps in flight at a time (its lanes): a caller that
+                                                     streams jobs keeps this many vx_submit_frames tickets outstanding */
 
 /* Pinned host memory helpers for the output ring / scan staging. */
 void* vx_host_alloc(size_t bytes);

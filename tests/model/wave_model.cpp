@@ -62,6 +62,30 @@ struct Model {
   std::vector<Parked> pool;
   std::vector<std::pair<size_t, uint32_t>> visit_log;  // (cell, owner) of every live visit of the pass
   uint64_t n_parked = 0, n_redo = 0;
+  // mode 2 (the product kernel since round 2): a memo mark is only ever READ by the snapshot of a LIVE cell, and a cell that
+  // is dead at the start of a pass stays dead for the pass -- so a ray skips the mark of every cell whose (2^s x 2^s x 1)
+  // block held no live cell when the pass began (`blive`, a superset of the live set at any later time of the pass)
+  std::vector<uint32_t> blive;
+  uint32_t bshift = 3;
+  uint64_t n_marks = 0, n_marks_skipped = 0;
+  size_t block_index(int32_t i, int32_t j, int32_t k) const {
+    const size_t bi = size_t(i) >> bshift, bj = size_t(j) >> bshift, nbj = (size_t(g.ny) >> bshift) + 1;
+    return (bi * nbj + bj) * size_t(g.nz) + size_t(k);
+  }
+  void build_blive() {
+    const size_t nbi = (size_t(g.nx) >> bshift) + 1, nbj = (size_t(g.ny) >> bshift) + 1;
+    blive.assign((nbi * nbj * size_t(g.nz) + 31) / 32, 0u);
+    for (int32_t i = 0; i < g.nx; ++i)
+      for (int32_t j = 0; j < g.ny; ++j)
+        for (int32_t k = 0; k < g.nz; ++k)
+          if (bit(live, lin(i, j, k))) setbit(blive, block_index(i, j, k), true);
+  }
+  bool mark_wanted(int32_t i, int32_t j, int32_t k) {
+    ++n_marks;
+    if (mode != 2 || bit(blive, block_index(i, j, k))) return true;
+    ++n_marks_skipped;
+    return false;
+  }
   // stats
   uint64_t n_rays = 0, n_steps = 0, n_waves = 0, n_resolve_waves = 0, n_rounds = 0, max_rounds = 0, n_prefix_steps = 0, n_unset = 0;
 
@@ -262,7 +286,7 @@ struct Model {
           h = true;
           break;
         }
-        memo[L] = std::max(memo[L], enc);
+        if (mark_wanted(r.i, r.j, r.k)) memo[L] = std::max(memo[L], enc);
         if (in_face) {
           const int32_t x = live_rank(r.i, r.j, r.k);
           if (x >= int32_t(rc)) owner[size_t(x)] = std::max(owner[size_t(x)], SET | id);
@@ -330,6 +354,7 @@ struct Model {
     const uint64_t rays0 = n_rays, steps0 = n_steps;
     for (;;) {
       bump_epoch();  // (a new epoch also forgets the marks of an abandoned attempt)
+      if (mode == 2) build_blive();
       std::fill(hit.begin(), hit.end(), 0);
       pool.clear();
       visit_log.clear();
@@ -376,6 +401,8 @@ void wm_run(const int32_t* size3, float res, const float* off3, const uint8_t* o
 }
 
 // mode 1: rays of the invalid passes in flight across waves.  extra2: rays parked, passes run again conservatively.
+// mode 2: memo marks filtered by the block-level live set of the pass start.  extra2: marks skipped, marks in all.
+// The block size is 2^(max_live >> 24) when that is non-zero (the upper byte of max_live; default 8 x 8 x 1).
 void wm_run_mode(int mode, const int32_t* size3, float res, const float* off3, const uint8_t* occ_bytes, uint32_t n_endpoints,
                  const float* endpoints, uint32_t max_live, uint64_t seed, uint8_t* occluded, uint8_t* invalid, uint64_t* stats8,
                  uint64_t* extra2) {
@@ -394,6 +421,8 @@ void wm_run_mode(int mode, const int32_t* size3, float res, const float* off3, c
   m.live.assign(words, 0);
   m.occl.assign(words, 0);
   m.memo.assign(m.nvox, 0);
+  if (max_live >> 24) m.bshift = max_live >> 24;
+  max_live &= 0xFFFFFFu;
   m.max_live = max_live < 1 ? 1 : max_live;
   m.rng = seed * 2 + 1;
   for (size_t L = 0; L < m.nvox; ++L)
@@ -421,8 +450,8 @@ void wm_run_mode(int mode, const int32_t* size3, float res, const float* off3, c
     stats8[7] = m.n_unset;
   }
   if (extra2) {
-    extra2[0] = m.n_parked;
-    extra2[1] = m.n_redo;
+    extra2[0] = mode == 2 ? m.n_marks_skipped : m.n_parked;
+    extra2[1] = mode == 2 ? m.n_marks : m.n_redo;
   }
 }
 

@@ -415,6 +415,51 @@ def test_async_submit_overlaps_uploads(orc, tmp_path):
     be.close()
 
 
+def test_several_jobs_and_batches_in_flight(tmp_path):
+    """The library keeps `batches_in_flight` batches (lanes) in flight: five jobs of three batches each, submitted back to back
+    under two scan id ranges, give the bytes of the synchronous call -- also when the histogram tables are far too small, so that
+    an overflow is met while other batches are in flight (everything in flight is redone with grown tables, oldest first)."""
+    seq = make_sequence(str(tmp_path / "seq"), 9, 32, 600)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    cfg = vx.Config(cfg_path("example"))
+
+    def specs_for(id_offset, order):
+        out = []
+        for target in order:
+            pb, pe, qb, qe = vx.window(cnt, cfg.pod.priorScans, cfg.pod.pastScans, target)
+            anchor = poses[pe - 1]
+            ap_p, _ = vx.frame_transforms(anchor, poses[pb:pe])
+            ap_q, ep = vx.frame_transforms(anchor, poses[qb:qe])
+            out.append(vx.FrameSpec(np.arange(pb, pe, dtype=np.uint32) + id_offset, ap_p, np.arange(qb, qe, dtype=np.uint32) + id_offset, ap_q, ep))
+        return out
+
+    ref = vx.Backend.from_config(cfg)
+    for t in range(cnt):
+        ref.upload_scan(t, scans[t], raw[t])
+    want = ref.process(specs_for(0, range(cnt)))
+    ref.close()
+    for kw in (dict(frames_in_flight=3), dict(frames_in_flight=3, table_log2_capacity=10)):
+        be = vx.Backend.from_config(cfg, **kw)
+        assert be.batches_in_flight >= 2
+        for t in range(cnt):
+            be.upload_scan(t, scans[t], raw[t])
+            be.upload_scan(500 + t, scans[t], raw[t])
+        jobs = []
+        for j in range(5):
+            order = list(range(cnt)) if j % 2 == 0 else list(range(cnt - 1, -1, -1))
+            outs = be.new_outputs(cnt)
+            arr, keep = be.build_descs(specs_for(500 * (j % 2), order), outs)
+            jobs.append((be.submit_descs(arr, cnt), order, outs))
+            del arr, keep
+        be.wait(jobs[2][0])
+        be.wait(0)
+        for _, order, outs in jobs:
+            for target, o in zip(order, outs):
+                for k in ("label", "bin", "occluded", "invalid"):
+                    assert np.array_equal(o[k], want[target][k]), (kw, target, k)
+        be.close()
+
+
 def test_thousand_frame_job_is_deterministic():
     """The benchmarked launch shape (>= 1036 frames = 7 CTAs on each of 148 SMs, RED.MAX / RED.OR marks racing in L2):
     the same job twice gives one sha256 over every output byte; set relations hold on a sample of frames."""

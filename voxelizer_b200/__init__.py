@@ -24,7 +24,7 @@ GEN_DATA_EXE = os.path.join(PKG, "bin", "vx_gen_data")
 # every symbol include/voxelizer_b200.h declares
 C_ABI_SYMBOLS = (
     "vx_last_global_error", "vx_last_error", "vx_device_count", "vx_create", "vx_destroy", "vx_grid_info_get",
-    "vx_frames_in_flight", "vx_host_alloc", "vx_host_free", "vx_upload_scan", "vx_upload_ticket", "vx_upload_wait",
+    "vx_frames_in_flight", "vx_batches_in_flight", "vx_host_alloc", "vx_host_free", "vx_upload_scan", "vx_upload_ticket", "vx_upload_wait",
     "vx_evict_scan", "vx_evict_all",
     "vx_process_frames", "vx_submit_frames", "vx_wait", "vx_sync", "vx_stage_times_get", "vx_stage_times_reset",
     "vx_debug_dump", "vx_trace_ray",
@@ -136,6 +136,8 @@ def cuda_lib():
         L.vx_grid_info_get.argtypes = [C.c_void_p, C.POINTER(GridInfo)]
         L.vx_frames_in_flight.restype = C.c_uint32
         L.vx_frames_in_flight.argtypes = [C.c_void_p]
+        L.vx_batches_in_flight.restype = C.c_uint32
+        L.vx_batches_in_flight.argtypes = [C.c_void_p]
         L.vx_host_alloc.restype = C.c_void_p
         L.vx_host_alloc.argtypes = [C.c_size_t]
         L.vx_host_free.argtypes = [C.c_void_p]
@@ -416,6 +418,7 @@ class Backend:
         self.packed_bytes = int(gi.packed_bytes)
         self.label_bytes = int(gi.label_bytes)
         self.frames_in_flight = int(L.vx_frames_in_flight(self._ctx))
+        self.batches_in_flight = int(L.vx_batches_in_flight(self._ctx))
 
     @classmethod
     def from_config(cls, cfg: Config, **kw):

@@ -74,11 +74,16 @@ struct Job {
   std::string error;
 };
 
-// One batch in flight.  Two lanes alternate, so that the next batch (of this or the next job) is filled, voted and
+// One batch in flight.  The lanes take turns, so that the next batches (of this or the next jobs) are filled, voted and
 // already tracing while the slowest frames of the previous one finish: a batch ends with its slowest frame (~1.2 x the mean
-// frame time), and CTAs of the next launch take the slots the finished frames leave.
+// frame time), and CTAs of the next launch take the slots the finished frames leave.  THREE lanes keep the device's traversal
+// slots full: while batch k ends and batch k + 1 holds most of the slots, batch k + 2 is already filled (its fill kernels
+// only get the few SM resources the resident traversal CTAs leave, so they must start a whole batch ahead).
+constexpr uint32_t kMaxLanes = 4;
 struct Lane {
   cudaStream_t stream = nullptr;
+  cudaStream_t fill_stream = nullptr;  // high-priority stream of the fill -> vote -> emit launches (null: they run on `stream`)
+  cudaEvent_t ev_staged = nullptr, ev_filled = nullptr;  // hand-over between the two streams
   cudaEvent_t ev[5]{};               // EV_BEGIN .. EV_END
   std::vector<cudaEvent_t> ev_sub;   // 4 per fill -> vote -> emit launch
   unsigned char* h_stage = nullptr;  // batch staging (items, ap, endpoints, vis frames): pinned host + device mirror
@@ -94,6 +99,19 @@ struct Lane {
   Job* job = nullptr;                // the job the batch belongs to
   std::unique_ptr<Job> owned;        // ... owned here if this is the job's last batch
 };
+
+// developer timeline (VX_B200_TRACE=<file>): one line per host-side event, CLOCK_REALTIME ns (the device's %globaltimer of
+// VX_B200_FRAME_STATS runs on the same clock)
+void trace_line(const char* what, unsigned long long a, unsigned long long b, const std::string& rest = std::string()) {
+  const char* path = std::getenv("VX_B200_TRACE");  // (read every time: a tool may switch files between contexts)
+  if (!path) return;
+  const unsigned long long now = (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                     std::chrono::system_clock::now().time_since_epoch()).count();
+  if (FILE* fp = std::fopen(path, "a")) {
+    std::fprintf(fp, "%s %llu %llu %llu %s\n", what, now, a, b, rest.c_str());
+    std::fclose(fp);
+  }
+}
 
 thread_local std::string* tl_error_sink = nullptr;  // set on the worker thread: errors belong to the job, not the context
 
@@ -145,9 +163,9 @@ struct vx_ctx {
   std::vector<UploadMark> marks;      // in upload order; completed ones are recycled
   std::vector<cudaEvent_t> ev_pool;   // timing-less events
 
-  Lane lanes[2];            // lanes[0].stream == stream
+  Lane lanes[kMaxLanes];    // lanes[0].stream == stream
   bool leave_room = false;  // see vx_launch_visibility
-  uint32_t depth = 1;       // batches in flight at a time (2 unless the tables are kept for debugging or memory is short)
+  uint32_t depth = 1;       // batches in flight at a time (3 unless the tables are kept for debugging or memory is short)
   uint32_t lane_cap = 0;    // frames per batch
   uint32_t next_lane = 0;
   uint64_t batch_seq = 0;
@@ -400,8 +418,10 @@ int wait_for_upload(vx_ctx* c, cudaStream_t st, uint64_t seq, bool* waited) {
 
 // Enqueues one batch of <= lane_cap frames on a lane: stage, fill -> vote -> emit per group, ONE traversal launch, pack, the
 // copies out.  Returns without waiting for the device (unless an output buffer is pageable memory: such a copy blocks).
-int enqueue_batch(vx_ctx* c, Lane& ln, Lane& other, const vx_frame_desc* frames, uint32_t nb) {
+// `prev` = the batch enqueued last if it is still in flight (null: none, or nothing of it may be waited for).
+int enqueue_batch(vx_ctx* c, Lane& ln, Lane* prev, const vx_frame_desc* frames, uint32_t nb) {
   const uint32_t base = ln.slot_base;
+  trace_line("enqueue_begin", c->batch_seq + 1, nb);
   int rc = ensure_slots(c, base, nb);
   if (rc != VX_OK) return rc;
   rc = ensure_scratch(c, nb);
@@ -503,8 +523,9 @@ int enqueue_batch(vx_ctx* c, Lane& ln, Lane& other, const vx_frame_desc* frames,
   }
   VX_CUDA(c, cudaMemcpyAsync(ln.d_stage, ln.h_stage, total, cudaMemcpyHostToDevice, st));
   VX_CUDA(c, cudaMemsetAsync(c->d_counters + (size_t)base * kCounterWords, 0, (size_t)nb * kCounterWords * sizeof(uint32_t), st));
-  // frames `table_sets` apart share histogram tables, across lanes too: this batch's first fill waits for the other batch's last emit
-  if (other.busy && other.n_sub) VX_CUDA(c, cudaStreamWaitEvent(st, other.ev_sub[4 * (other.n_sub - 1) + 3], 0));
+  // frames `table_sets` apart share histogram tables, across lanes too: this batch's first fill waits for the last emit of the
+  // batch enqueued before it (which waited for its own predecessor: the chain orders every batch in flight)
+  if (prev && prev->busy && prev->n_sub) VX_CUDA(c, cudaStreamWaitEvent(st, prev->ev_sub[4 * (prev->n_sub - 1) + 3], 0));
 
   const VxScanWork* d_works = reinterpret_cast<const VxScanWork*>(ln.d_stage + off_works);
   const VxScanUse* d_uses = reinterpret_cast<const VxScanUse*>(ln.d_stage + off_uses);
@@ -526,32 +547,43 @@ int enqueue_batch(vx_ctx* c, Lane& ln, Lane& other, const vx_frame_desc* frames,
   uint64_t fill_launches = 0;
   const uint32_t n_scratch = (uint32_t)c->scratch.size();
   VX_CUDA(c, cudaEventRecord(ln.ev[EV_BEGIN], st));
+  // The short fill / vote / emit kernels run on a HIGH-PRIORITY stream of the lane: when a traversal CTA of an older batch
+  // retires, the SM resources it leaves go to them before they go to the ~900 queued traversal CTAs of the batch in between.
+  cudaStream_t fs = ln.fill_stream ? ln.fill_stream : st;
+  if (fs != st) {
+    VX_CUDA(c, cudaEventRecord(ln.ev_staged, st));
+    VX_CUDA(c, cudaStreamWaitEvent(fs, ln.ev_staged, 0));
+  }
   for (uint32_t g = 0; g < n_sub; ++g) {
     const uint32_t f0 = g * c->table_sets, f1 = f0 + c->table_sets < nb ? f0 + c->table_sets : nb;
     const uint32_t n_works = (uint32_t)(work_begin[g + 1] - work_begin[g]);
     bool waited = false;
-    rc2 = wait_for_upload(c, st, sub_need_seq[g], &waited);
+    rc2 = wait_for_upload(c, fs, sub_need_seq[g], &waited);
     if (rc2 != VX_OK) return rc2;
-    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 0], st));
-    VX_CUDA(c, vx_launch_fill(d_works + work_begin[g], n_works, sub_max_points[g], d_uses, d_ap, c->d_slots + base, c->geom, c->filter, st));
-    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 1], st));
-    VX_CUDA(c, vx_launch_vote(c->d_slots + base + f0, f1 - f0, c->nvox, st));
-    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 2], st));
-    VX_CUDA(c, vx_launch_emit(c->d_slots + base + f0, f1 - f0, c->keep_tables ? 1 : 0, st));
-    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 3], st));
+    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 0], fs));
+    VX_CUDA(c, vx_launch_fill(d_works + work_begin[g], n_works, sub_max_points[g], d_uses, d_ap, c->d_slots + base, c->geom, c->filter, fs));
+    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 1], fs));
+    VX_CUDA(c, vx_launch_vote(c->d_slots + base + f0, f1 - f0, c->nvox, fs));
+    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 2], fs));
+    VX_CUDA(c, vx_launch_emit(c->d_slots + base + f0, f1 - f0, c->keep_tables ? 1 : 0, fs));
+    VX_CUDA(c, cudaEventRecord(ln.ev_sub[4 * g + 3], fs));
     fill_launches += (n_works + 65534) / 65535;
+  }
+  if (fs != st) {
+    VX_CUDA(c, cudaEventRecord(ln.ev_filled, fs));
+    VX_CUDA(c, cudaStreamWaitEvent(st, ln.ev_filled, 0));
   }
   // ONE visibility launch per batch.  (Measured: a launch per group on streams of their own, started as soon as the
   // group is filled, is slower -- every launch places its CTAs on the SMs in the same order, so 8 launches of 114
   // CTAs load 114 SMs with 7 CTAs and leave 34 idle; with groups of 148 it still lost 6 % to the single launch.)
   int leave_room = 0;  // VX_B200_LEAVE_ROOM=1 (developer switch, A/B): 6 traversal CTAs per SM while another batch is in flight / queued
-  if (c->leave_room && c->depth == 2) {
+  if (c->leave_room && c->depth >= 2) {
     bool queued = false;
     {
       std::lock_guard<std::mutex> qk(c->qmu);
       queued = !c->queue.empty();
     }
-    leave_room = (other.busy || queued) ? 1 : 0;
+    leave_room = ((prev && prev->busy) || queued) ? 1 : 0;
   }
   VX_CUDA(c, cudaEventRecord(ln.ev[EV_VIS_BEGIN], st));
   VX_CUDA(c, vx_launch_visibility(c->d_slots + base, d_vis, nb, d_ep, c->geom, c->d_scratch, n_scratch, c->d_locks, c->vis_mode, leave_room, st));
@@ -603,6 +635,7 @@ int enqueue_batch(vx_ctx* c, Lane& ln, Lane& other, const vx_frame_desc* frames,
   VX_CUDA(c, cudaEventRecord(ln.ev[EV_END], st));
   ln.busy = true;
   ln.seq = ++c->batch_seq;
+  trace_line("enqueue_end", ln.seq, nb);
   ln.frames = frames;
   ln.nb = nb;
   ln.n_sub = n_sub;
@@ -619,6 +652,19 @@ int finish_batch(vx_ctx* c, Lane& ln) {
   const uint64_t points = ln.points, fill_launches = ln.fill_launches;
   NvtxRange nvtx_wait("vx:wait");
   VX_CUDA(c, cudaStreamSynchronize(ln.stream));
+  if (std::getenv("VX_B200_TRACE")) {  // stage boundaries of the batch, ms after its EV_BEGIN
+    float a = 0, b = 0, v0 = 0, v1 = 0, e1 = 0;
+    if (n_sub) {
+      cudaEventElapsedTime(&a, ln.ev[EV_BEGIN], ln.ev_sub[0]);
+      cudaEventElapsedTime(&b, ln.ev[EV_BEGIN], ln.ev_sub[4 * (n_sub - 1) + 3]);
+    }
+    cudaEventElapsedTime(&v0, ln.ev[EV_BEGIN], ln.ev[EV_VIS_BEGIN]);
+    cudaEventElapsedTime(&v1, ln.ev[EV_BEGIN], ln.ev[EV_VIS]);
+    cudaEventElapsedTime(&e1, ln.ev[EV_BEGIN], ln.ev[EV_END]);
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "first_fill %.1f last_emit %.1f vis_begin %.1f vis_end %.1f end %.1f", a, b, v0, v1, e1);
+    trace_line("retire", ln.seq, nb, buf);
+  }
   if (c->keep_tables) {
     c->tables_dirty = true;
     c->dirty_slots = nb;
@@ -641,6 +687,7 @@ int finish_batch(vx_ctx* c, Lane& ln) {
   // occupied cells << 32
   if (const char* path = std::getenv("VX_B200_FRAME_STATS")) {
     if (FILE* fp = std::fopen(path, "a")) {
+      std::fprintf(fp, "# batch %llu\n", (unsigned long long)ln.seq);
       for (uint32_t f = 0; f < nb; ++f) {
         unsigned long long rs[VX_SLOT_STATS];
         std::memcpy(rs, c->h_counters + (size_t)(base + f) * kCounterWords + 4, sizeof(rs));
@@ -698,8 +745,15 @@ void evict_locked(vx_ctx* c, uint32_t scan_id) {
 
 Lane* oldest_busy(vx_ctx* c) {
   Lane* best = nullptr;
-  for (uint32_t k = 0; k < 2; ++k)
+  for (uint32_t k = 0; k < kMaxLanes; ++k)
     if (c->lanes[k].busy && (!best || c->lanes[k].seq < best->seq)) best = &c->lanes[k];
+  return best;
+}
+
+Lane* newest_busy(vx_ctx* c) {
+  Lane* best = nullptr;
+  for (uint32_t k = 0; k < kMaxLanes; ++k)
+    if (c->lanes[k].busy && (!best || c->lanes[k].seq > best->seq)) best = &c->lanes[k];
   return best;
 }
 
@@ -726,8 +780,10 @@ void settle_batch(vx_ctx* c, Lane& ln, int rc, const std::string& error) {
 
 int grow_tables(vx_ctx* c) {  // x4; every lane is idle
   if (c->log2_target >= 28) return fail(c, VX_ERR_TABLE_OVERFLOW, "histogram table overflow at 2^28 slots");
-  for (uint32_t k = 0; k < 2; ++k)
+  for (uint32_t k = 0; k < kMaxLanes; ++k) {
     if (c->lanes[k].stream) VX_CUDA(c, cudaStreamSynchronize(c->lanes[k].stream));
+    if (c->lanes[k].fill_stream) VX_CUDA(c, cudaStreamSynchronize(c->lanes[k].fill_stream));
+  }
   free_slots(c);
   c->log2_target += 2;
   c->log2_input = c->log2_target > 12 ? c->log2_target - 3 : c->log2_target;
@@ -737,8 +793,9 @@ int grow_tables(vx_ctx* c) {  // x4; every lane is idle
   return VX_OK;
 }
 
-// Completes the oldest batch in flight.  If its tables overflowed, the other lane is completed too (the tables are rebuilt), the
-// tables grow and the overflowed batches run again, one at a time; everything is settled oldest first.
+// Completes the oldest batch in flight.  If its tables overflowed, every other lane is completed too (the tables are rebuilt and
+// the frame records go with them), the tables grow and the batches run again, one at a time and oldest first; then everything is
+// settled, oldest first.
 void retire_oldest(vx_ctx* c) {
   Lane* ln = oldest_busy(c);
   if (!ln) return;
@@ -750,40 +807,42 @@ void retire_oldest(vx_ctx* c) {
     settle_batch(c, *ln, rc, err);
     return;
   }
-  Lane* newer = nullptr;
-  for (uint32_t k = 0; k < 2; ++k)
-    if (c->lanes[k].busy && &c->lanes[k] != ln) newer = &c->lanes[k];
-  std::string err2;
-  int rc2 = VX_OK;
-  if (newer) {
-    tl_error_sink = &err2;
-    rc2 = finish_batch(c, *newer);
+  struct Redo {
+    Lane* lane;
+    int rc;
+    std::string err;
+  };
+  std::vector<Redo> newer;  // the other batches in flight, oldest first
+  for (uint32_t k = 0; k < kMaxLanes; ++k)
+    if (c->lanes[k].busy && &c->lanes[k] != ln) newer.push_back(Redo{&c->lanes[k], VX_OK, std::string()});
+  std::sort(newer.begin(), newer.end(), [](const Redo& a, const Redo& b) { return a.lane->seq < b.lane->seq; });
+  for (Redo& r : newer) {
+    tl_error_sink = &r.err;
+    r.rc = finish_batch(c, *r.lane);
   }
   auto rerun = [&](Lane& l, std::string& e, bool grow_first) {
     tl_error_sink = &e;
     for (bool grow = grow_first;; grow = true) {
       int r = grow ? grow_tables(c) : VX_OK;
       if (r != VX_OK) return r;
-      l.busy = false;  // (enqueue_batch must not wait for this lane's own stale events)
-      Lane& o = &l == &c->lanes[0] ? c->lanes[1] : c->lanes[0];
-      const bool o_busy = o.busy;
-      o.busy = false;
-      r = enqueue_batch(c, l, o, l.frames, l.nb);
-      o.busy = o_busy;
-      l.busy = true;
+      // (every lane is idle here -- finish_batch waited for each -- and nothing of another batch is waited for: prev = null)
+      r = enqueue_batch(c, l, nullptr, l.frames, l.nb);
       if (r != VX_OK) return r;
       r = finish_batch(c, l);
       if (r != VX_ERR_TABLE_OVERFLOW) return r;
     }
   };
   rc = rerun(*ln, err, true);
-  if (newer && (rc2 == VX_ERR_TABLE_OVERFLOW || rc2 == VX_OK)) {
-    // the frame records of the newer batch went with the old tables: run it again whatever it said
-    rc2 = rerun(*newer, err2, false);
+  for (Redo& r : newer) {
+    // the frame records of the newer batches went with the old tables: run them again whatever they said (a CUDA error stays)
+    if (r.rc == VX_ERR_TABLE_OVERFLOW || r.rc == VX_OK) {
+      r.err.clear();
+      r.rc = rerun(*r.lane, r.err, false);
+    }
   }
   tl_error_sink = nullptr;
   settle_batch(c, *ln, rc, err);
-  if (newer) settle_batch(c, *newer, rc2, err2);
+  for (Redo& r : newer) settle_batch(c, *r.lane, r.rc, r.err);
 }
 
 // Enqueues every batch of a job; its last batch stays in flight (the job is published when that batch is settled).
@@ -811,14 +870,14 @@ void run_job(vx_ctx* c, std::unique_ptr<Job> job) {
   for (uint32_t base = 0; base < n;) {
     const uint32_t nb = n - base < per_batch ? n - base : per_batch;
     Lane& ln = c->lanes[c->next_lane];
-    Lane& other = c->lanes[c->next_lane ^ 1u];
     while (ln.busy) retire_oldest(c);
     if (j->rc != VX_OK) return abandon(j->rc, j->error);  // an earlier batch of this job failed
     std::string err;
     tl_error_sink = &err;
-    const int rc = enqueue_batch(c, ln, other, j->frames.data() + base, nb);
+    const int rc = enqueue_batch(c, ln, newest_busy(c), j->frames.data() + base, nb);
     tl_error_sink = nullptr;
     if (rc != VX_OK) {
+      if (ln.fill_stream) cudaStreamSynchronize(ln.fill_stream);
       cudaStreamSynchronize(ln.stream);
       return abandon(rc, err);
     }
@@ -918,9 +977,24 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
     c->own_stream = true;
   }
   c->lanes[0].stream = c->stream;
-  VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->lanes[1].stream, cudaStreamNonBlocking));
-  for (uint32_t k = 0; k < 2; ++k)
-    for (int i = 0; i < EV_COUNT; ++i) VX_CREATE_CUDA(cudaEventCreate(&c->lanes[k].ev[i]));
+  {
+    // developer switches (A/B on the device): VX_B200_LANES = batches in flight (1 .. 4, default 3), VX_B200_FILL_PRIO=0 keeps
+    // the fill / vote / emit kernels on the lane's own stream
+    int lo_prio = 0, hi_prio = 0;
+    VX_CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    const char* e = std::getenv("VX_B200_FILL_PRIO");
+    const bool fill_prio = (!e || std::atoi(e) != 0) && hi_prio < lo_prio;
+    for (uint32_t k = 0; k < kMaxLanes; ++k) {
+      Lane& ln = c->lanes[k];
+      if (k > 0) VX_CREATE_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+      for (int i = 0; i < EV_COUNT; ++i) VX_CREATE_CUDA(cudaEventCreate(&ln.ev[i]));
+      if (fill_prio) {
+        VX_CREATE_CUDA(cudaStreamCreateWithPriority(&ln.fill_stream, cudaStreamNonBlocking, hi_prio));
+        VX_CREATE_CUDA(cudaEventCreateWithFlags(&ln.ev_staged, cudaEventDisableTiming));
+        VX_CREATE_CUDA(cudaEventCreateWithFlags(&ln.ev_filled, cudaEventDisableTiming));
+      }
+    }
+  }
   VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
   VX_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
   VX_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_copy_out, cudaEventDisableTiming));
@@ -998,10 +1072,14 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   uint32_t want = options && options->frames_in_flight ? options->frames_in_flight : 4u * resident;
   if (c->keep_tables && want > 8u && !(options && options->frames_in_flight)) want = 8u;  // debug: small batches,
   if (c->keep_tables || want < c->table_sets) c->table_sets = want;                       // every frame its own tables
-  // Two batches in flight (two lanes, each with frame records for a whole batch) unless the tables are kept for debugging or a
-  // scratch buffer per resident CTA (needed once CTAs of two launches share the SMs) does not fit next to everything else.
+  // Three batches in flight (three lanes, each with frame records for a whole batch) unless the tables are kept for debugging or
+  // a scratch buffer per resident CTA (needed once CTAs of several launches share the SMs) does not fit next to everything else.
   if (const char* e = std::getenv("VX_B200_LEAVE_ROOM")) c->leave_room = std::atoi(e) != 0;
-  c->depth = 2;
+  c->depth = 3;
+  if (const char* e = std::getenv("VX_B200_LANES")) {
+    const int n = std::atoi(e);
+    if (n >= 1 && n <= (int)kMaxLanes) c->depth = (uint32_t)n;
+  }
   if (c->keep_tables || (size_t)resident * scratch_bytes(c) > free_b / 4) c->depth = 1;
   {  // the largest batch whose frame records, histogram tables and traversal scratch fit into 70 % of the free memory
      // (scratch: one buffer per RESIDENT CTA -- at most one per frame with one lane; tables: one set per frame of a fill group)
@@ -1018,8 +1096,7 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   if (c->table_sets > want) c->table_sets = want;
   c->lane_cap = want;                 // frames per batch
   c->max_slots = c->depth * want;     // frame records (allocated as batches need them)
-  c->lanes[0].slot_base = 0;
-  c->lanes[1].slot_base = c->lane_cap;
+  for (uint32_t k = 0; k < kMaxLanes; ++k) c->lanes[k].slot_base = k * c->lane_cap;  // (lanes >= depth are never used)
   VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_slots), (size_t)c->max_slots * sizeof(VxSlot)));
   VX_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_counters), (size_t)c->max_slots * kCounterWords * sizeof(uint32_t)));
   VX_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_counters), (size_t)c->max_slots * kCounterWords * sizeof(uint32_t)));
@@ -1039,8 +1116,11 @@ void vx_destroy(vx_ctx* c) {
     c->worker.join();
   }
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->lanes[1].stream) cudaStreamSynchronize(c->lanes[1].stream);
+  for (uint32_t k = 0; k < kMaxLanes; ++k) {
+    if (c->lanes[k].fill_stream) cudaStreamSynchronize(c->lanes[k].fill_stream);
+    if (c->lanes[k].stream) cudaStreamSynchronize(c->lanes[k].stream);
+  }
+  if (c->copy_out) cudaStreamSynchronize(c->copy_out);
   if (c->copy_in) cudaStreamSynchronize(c->copy_in);
   free_slots(c);
   for (auto& kv : c->scans) {
@@ -1057,15 +1137,18 @@ void vx_destroy(vx_ctx* c) {
   for (void* p : c->scratch_slabs) cudaFree(p);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_locks) cudaFree(c->d_locks);
-  for (uint32_t k = 0; k < 2; ++k) {
+  for (uint32_t k = 0; k < kMaxLanes; ++k) {
     Lane& ln = c->lanes[k];
     for (cudaEvent_t e : ln.ev_sub) cudaEventDestroy(e);
     for (int i = 0; i < EV_COUNT; ++i)
       if (ln.ev[i]) cudaEventDestroy(ln.ev[i]);
+    if (ln.ev_staged) cudaEventDestroy(ln.ev_staged);
+    if (ln.ev_filled) cudaEventDestroy(ln.ev_filled);
     if (ln.h_stage) cudaFreeHost(ln.h_stage);
     if (ln.d_stage) cudaFree(ln.d_stage);
+    if (ln.fill_stream) cudaStreamDestroy(ln.fill_stream);
+    if (k > 0 && ln.stream) cudaStreamDestroy(ln.stream);
   }
-  if (c->lanes[1].stream) cudaStreamDestroy(c->lanes[1].stream);
   if (c->d_slots) cudaFree(c->d_slots);
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1090,6 +1173,7 @@ int vx_grid_info_get(const vx_ctx* c, vx_grid_info* out) {
 }
 
 uint32_t vx_frames_in_flight(const vx_ctx* c) { return c ? c->lane_cap : 0; }
+uint32_t vx_batches_in_flight(const vx_ctx* c) { return c ? c->depth : 0; }
 
 int vx_upload_scan(vx_ctx* c, uint32_t scan_id, const float* xyzr, const uint32_t* labels, uint32_t n) {
   if (!c || (n && (!xyzr || !labels))) return fail(c, VX_ERR_INVALID, "null argument");
@@ -1206,6 +1290,7 @@ int vx_submit_frames(vx_ctx* c, const vx_frame_desc* frames, uint32_t n, uint64_
     if (!c->worker.joinable()) c->worker = std::thread(worker_main, c);
     job->ticket = c->next_ticket++;
     *ticket = job->ticket;
+    trace_line("submit", job->ticket, n);
     c->queue.push_back(std::move(job));
   }
   c->qcv.notify_one();
@@ -1241,8 +1326,8 @@ int vx_sync(vx_ctx* c) {
   const int rc = vx_wait(c, 0);
   VX_CUDA(c, cudaSetDevice(c->device));
   VX_CUDA(c, cudaStreamSynchronize(c->copy_in));
-  VX_CUDA(c, cudaStreamSynchronize(c->stream));
-  VX_CUDA(c, cudaStreamSynchronize(c->lanes[1].stream));
+  for (uint32_t k = 0; k < kMaxLanes; ++k)
+    if (c->lanes[k].stream) VX_CUDA(c, cudaStreamSynchronize(c->lanes[k].stream));
   std::lock_guard<std::mutex> lk(c->mu);
   prune_marks(c);
   return rc;
