@@ -75,7 +75,8 @@ typedef struct vx_options {
                                     histogram tables (default 128) */
   uint32_t vis_mode;             /* shape of the traversal kernel: 0 = chosen per batch (few frames: one 512-thread CTA per SM and
                                     whole-face waves, short time per frame; many frames: 7 x 128-thread CTAs per SM, most frames per
-                                    second), 1 = always the many-frames shape, 2 = always the few-frames shape.  Same bytes either way. */
+                                    second), 1 = always the many-frames shape, 2 = always the few-frames shape, 3 = the shape in between (4 x 256-thread
+                                    CTAs per SM).  Same bytes either way. */
   uint32_t occlusion_labels;     /* 1: frames may ask for VoxelGrid::insertOcclusionLabels (VX_FRAME_INSERT_OCCLUSION_LABELS); costs 8 bytes per
                                     voxel and frame of a batch, and 4 per visit of the traversal's scratch */
 } vx_options;

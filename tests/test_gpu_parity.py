@@ -23,10 +23,11 @@ def orc(request):
     return Oracle(request.param)
 
 
-@pytest.fixture(params=[1, 2], ids=["throughput-shape", "latency-shape"])
+@pytest.fixture(params=[1, 2, 3], ids=["throughput-shape", "latency-shape", "middle-shape"])
 def vis_mode(request):
-    """Both shapes of the traversal kernel (vx_options.vis_mode): 7 x 128-thread CTAs per SM with waves of <= 1280 live cells,
-    and one 512-thread CTA per SM with whole-face waves.  Left to itself the library picks by batch size."""
+    """The three shapes of the traversal kernel (vx_options.vis_mode): 7 x 128-thread CTAs per SM with waves of <= 1280 live cells,
+    one 512-thread CTA per SM with whole-face waves, and 4 x 256-thread CTAs per SM with waves of <= 2560 live cells.  Left to
+    itself the library picks by batch size."""
     return request.param
 
 
@@ -415,6 +416,46 @@ def test_async_submit_overlaps_uploads(orc, tmp_path):
     be.close()
 
 
+def test_outputs_in_a_ring_leave_as_2d_copies(tmp_path):
+    """Host buffers that are evenly spaced (an output ring) are copied out with one 2-D copy per run of frames instead of four
+    copies per frame: whatever the placement (in order, partly reversed, with a gap), the bytes are those of separate arrays."""
+    seq = make_sequence(str(tmp_path / "seq"), 12, 32, 500)
+    cnt, poses, scans, labels, raw = _load_sequence(seq)
+    cfg = vx.Config(cfg_path("example"))
+    specs = []
+    for target in range(cnt):
+        pb, pe, qb, qe = vx.window(cnt, cfg.pod.priorScans, cfg.pod.pastScans, target)
+        anchor = poses[pe - 1]
+        ap_p, _ = vx.frame_transforms(anchor, poses[pb:pe])
+        ap_q, ep = vx.frame_transforms(anchor, poses[qb:qe])
+        specs.append(vx.FrameSpec(np.arange(pb, pe, dtype=np.uint32), ap_p, np.arange(qb, qe, dtype=np.uint32), ap_q, ep))
+    be = vx.Backend.from_config(cfg, table_sets=5)
+    for t in range(cnt):
+        be.upload_scan(t, scans[t], raw[t])
+    want = be.process(specs)
+    per = be.label_bytes + 3 * be.packed_bytes
+    for place in (list(range(cnt)), [0, 1, 2, 5, 4, 3, 6, 7, 9, 11, 13, 14]):
+        ring = vx.PinnedBuffer((max(place) + 1) * per)
+        ring.array[:] = 0xAB
+        outs = []
+        for k in place:
+            b = ring.array[k * per:(k + 1) * per]
+            outs.append(dict(label=b[:be.label_bytes], bin=b[be.label_bytes:be.label_bytes + be.packed_bytes],
+                             occluded=b[be.label_bytes + be.packed_bytes:be.label_bytes + 2 * be.packed_bytes],
+                             invalid=b[be.label_bytes + 2 * be.packed_bytes:]))
+        arr, keep = be.build_descs(specs, outs)
+        be.process_descs(arr, cnt)
+        for f in range(cnt):
+            for k in ("label", "bin", "occluded", "invalid"):
+                assert np.array_equal(outs[f][k].view(np.uint8), want[f][k].view(np.uint8)), (place[f], k)
+        used = set(place)
+        for k in range(max(place) + 1):
+            if k not in used:
+                assert (ring.array[k * per:(k + 1) * per] == 0xAB).all(), "a slot no frame owns was written"
+        ring.free()
+    be.close()
+
+
 def test_several_jobs_and_batches_in_flight(tmp_path):
     """The library keeps `batches_in_flight` batches (lanes) in flight: five jobs of three batches each, submitted back to back
     under two scan id ranges, give the bytes of the synchronous call -- also when the histogram tables are far too small, so that
@@ -493,6 +534,13 @@ def test_thousand_frame_job_is_deterministic():
                 h.update(o[k].tobytes())
         digests.append(h.hexdigest())
     assert digests[0] == digests[1]
+    # the first 560 frames alone: a batch of 2 - 4 frames per SM runs in the MIDDLE shape (4 x 256-thread CTAs per SM, all of them
+    # resident at once) -- same bytes as the throughput shape gave above
+    part = be.process(specs[:560])
+    for a, b in zip(part, outs[:560]):
+        for k in ("bin", "label", "occluded", "invalid"):
+            assert np.array_equal(a[k], b[k]), k
+    del part
     for o in outs[::97]:
         occl = np.unpackbits(o["occluded"], bitorder="big").astype(bool)
         inv = np.unpackbits(o["invalid"], bitorder="big").astype(bool)

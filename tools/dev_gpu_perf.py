@@ -16,7 +16,7 @@ params = vx.synth_params()
 xyzr = np.empty((n_scans, CAP, 4), np.float32); lab = np.empty((n_scans, CAP), np.uint32)
 counts = vx.synth_generate_many(params, 0, n_scans, xyzr.ctypes.data, lab.ctypes.data, CAP)
 poses = vx.synth_velo_poses(params, n_scans).astype(np.float32)
-be = vx.Backend.from_config(cfg, frames_in_flight=fif)
+be = vx.Backend.from_config(cfg, frames_in_flight=fif, vis_mode=int(os.environ.get("VX_DEV_VIS_MODE", "0")))
 for t in range(n_scans):
     be.upload_scan(t, xyzr[t, :counts[t]], lab[t, :counts[t]])
 specs = []

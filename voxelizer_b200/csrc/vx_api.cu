@@ -76,9 +76,8 @@ struct Job {
 
 // One batch in flight.  The lanes take turns, so that the next batches (of this or the next jobs) are filled, voted and
 // already tracing while the slowest frames of the previous one finish: a batch ends with its slowest frame (~1.2 x the mean
-// frame time), and CTAs of the next launch take the slots the finished frames leave.  THREE lanes keep the device's traversal
-// slots full: while batch k ends and batch k + 1 holds most of the slots, batch k + 2 is already filled (its fill kernels
-// only get the few SM resources the resident traversal CTAs leave, so they must start a whole batch ahead).
+// frame time), and CTAs of the next launch take the slots the finished frames leave.  Two lanes by default; up to kMaxLanes
+// (VX_B200_LANES, a developer switch: measured, the traversal slots are full with two).
 constexpr uint32_t kMaxLanes = 4;
 struct Lane {
   cudaStream_t stream = nullptr;
@@ -165,7 +164,7 @@ struct vx_ctx {
 
   Lane lanes[kMaxLanes];    // lanes[0].stream == stream
   bool leave_room = false;  // see vx_launch_visibility
-  uint32_t depth = 1;       // batches in flight at a time (3 unless the tables are kept for debugging or memory is short)
+  uint32_t depth = 1;       // batches in flight at a time (2 unless the tables are kept for debugging or memory is short)
   uint32_t lane_cap = 0;    // frames per batch
   uint32_t next_lane = 0;
   uint64_t batch_seq = 0;
@@ -597,34 +596,90 @@ int enqueue_batch(vx_ctx* c, Lane& ln, Lane* prev, const vx_frame_desc* frames, 
 
   // Copy-out.  Everything above is enqueued by now: a copy into pageable memory blocks the host, never the device.
   // `.label` / `.bin` are final after a group's emit: they leave on the copy stream while the rays are traced.
+  // ONE 2-D copy per run of frames whose host buffers are evenly spaced (an output ring) and whose frame records are too (carved
+  // from one slab): a 909-frame batch used to queue 3636 copies, most of them behind the traversal kernel, and a stream takes
+  // only ~1000 pending operations before the enqueueing call blocks -- measured: vx_submit_frames' worker sat in this loop until
+  // the batch was nearly over, so batches with host outputs never overlapped (profiles/r02_e2e_timeline_before.txt).
   const size_t packed = (size_t)(c->nvox / 8);
+  enum { OUT_LABEL = 0, OUT_BIN, OUT_OCCLUDED, OUT_INVALID };
+  auto host_ptr = [&](uint32_t f, int kind) -> unsigned char* {
+    const vx_frame_desc& fr = frames[f];
+    void* p = kind == OUT_LABEL ? (void*)fr.out_label : kind == OUT_BIN ? (void*)fr.out_bin : kind == OUT_OCCLUDED ? (void*)fr.out_occluded : (void*)fr.out_invalid;
+    return static_cast<unsigned char*>(p);
+  };
+  auto dev_ptr = [&](uint32_t f, int kind) -> const unsigned char* {
+    const VxSlot& sl = c->slots[base + f].dev;
+    const void* p = kind == OUT_LABEL ? (const void*)sl.out_label : kind == OUT_BIN ? (const void*)sl.out_bin : kind == OUT_OCCLUDED ? (const void*)sl.out_occluded : (const void*)sl.out_invalid;
+    return static_cast<const unsigned char*>(p);
+  };
+  // frames [f0, f1) for which want(f) holds and the host buffer exists; returns the number of frames copied
+  auto copy_out_kind = [&](uint32_t f0, uint32_t f1, int kind, cudaStream_t to, auto want, uint32_t* copied) -> cudaError_t {
+    const size_t bytes = kind == OUT_LABEL ? (size_t)c->nvox * 2 : packed;
+    const ptrdiff_t max_pitch = 0x7FFFFFFF;
+    unsigned char *h0 = nullptr, *hprev = nullptr;
+    const unsigned char *d0 = nullptr, *dprev = nullptr;
+    ptrdiff_t hs = 0, ds = 0;
+    uint32_t run = 0;
+    auto flush = [&]() -> cudaError_t {
+      cudaError_t e = cudaSuccess;
+      if (run == 1) e = cudaMemcpyAsync(h0, d0, bytes, cudaMemcpyDeviceToHost, to);
+      else if (run > 1) e = cudaMemcpy2DAsync(h0, (size_t)hs, d0, (size_t)ds, bytes, run, cudaMemcpyDeviceToHost, to);
+      run = 0;
+      return e;
+    };
+    for (uint32_t f = f0; f < f1; ++f) {
+      unsigned char* hp = want(f) ? host_ptr(f, kind) : nullptr;
+      if (!hp) {  // a frame that is left out ends the run (rows of a 2-D copy are consecutive)
+        const cudaError_t e = flush();
+        if (e != cudaSuccess) return e;
+        continue;
+      }
+      const unsigned char* dp = dev_ptr(f, kind);
+      ++*copied;
+      if (run == 1) {
+        hs = hp - hprev;
+        ds = dp - dprev;
+        if (hs >= (ptrdiff_t)bytes && ds >= (ptrdiff_t)bytes && hs <= max_pitch && ds <= max_pitch) {
+          run = 2;
+          hprev = hp;
+          dprev = dp;
+          continue;
+        }
+      } else if (run > 1 && hp - hprev == hs && dp - dprev == ds) {
+        ++run;
+        hprev = hp;
+        dprev = dp;
+        continue;
+      }
+      const cudaError_t e = flush();
+      if (e != cudaSuccess) return e;
+      h0 = hprev = hp;
+      d0 = dprev = dp;
+      run = 1;
+    }
+    return flush();
+  };
   bool any_early = false;
+  auto early = [&](uint32_t f) { return (frames[f].flags & VX_FRAME_INSERT_OCCLUSION_LABELS) == 0; };
+  auto late_labels = [&](uint32_t f) { return (frames[f].flags & VX_FRAME_INSERT_OCCLUSION_LABELS) != 0; };  // they change during the traversal
+  auto every = [&](uint32_t) { return true; };
   for (uint32_t g = 0; g < n_sub; ++g) {
     const uint32_t f0 = g * c->table_sets, f1 = f0 + c->table_sets < nb ? f0 + c->table_sets : nb;
-    bool first = true;
-    for (uint32_t f = f0; f < f1; ++f) {
-      const vx_frame_desc& fr = frames[f];
-      if (!fr.out_label && !fr.out_bin) continue;
-      if (fr.flags & VX_FRAME_INSERT_OCCLUSION_LABELS) continue;  // its labels change during the traversal: copied below
-      if (first) {
-        VX_CUDA(c, cudaStreamWaitEvent(c->copy_out, ln.ev_sub[4 * g + 3], 0));
-        first = false;
-        any_early = true;
-      }
-      const VxSlot& s = c->slots[base + f].dev;
-      if (fr.out_label) VX_CUDA(c, cudaMemcpyAsync(fr.out_label, s.out_label, (size_t)c->nvox * 2, cudaMemcpyDeviceToHost, c->copy_out));
-      if (fr.out_bin) VX_CUDA(c, cudaMemcpyAsync(fr.out_bin, s.out_bin, packed, cudaMemcpyDeviceToHost, c->copy_out));
-    }
+    bool any = false;
+    for (uint32_t f = f0; f < f1 && !any; ++f) any = early(f) && (frames[f].out_label || frames[f].out_bin);
+    if (!any) continue;
+    any_early = true;
+    uint32_t n_copied = 0;
+    VX_CUDA(c, cudaStreamWaitEvent(c->copy_out, ln.ev_sub[4 * g + 3], 0));
+    VX_CUDA(c, copy_out_kind(f0, f1, OUT_LABEL, c->copy_out, early, &n_copied));
+    VX_CUDA(c, copy_out_kind(f0, f1, OUT_BIN, c->copy_out, early, &n_copied));
   }
-  for (uint32_t f = 0; f < nb; ++f) {
-    const vx_frame_desc& fr = frames[f];
-    const VxSlot& s = c->slots[base + f].dev;
-    if (fr.flags & VX_FRAME_INSERT_OCCLUSION_LABELS) {
-      if (fr.out_label) VX_CUDA(c, cudaMemcpyAsync(fr.out_label, s.out_label, (size_t)c->nvox * 2, cudaMemcpyDeviceToHost, st));
-      if (fr.out_bin) VX_CUDA(c, cudaMemcpyAsync(fr.out_bin, s.out_bin, packed, cudaMemcpyDeviceToHost, st));
-    }
-    if (fr.out_occluded) VX_CUDA(c, cudaMemcpyAsync(fr.out_occluded, s.out_occluded, packed, cudaMemcpyDeviceToHost, st));
-    if (fr.out_invalid) VX_CUDA(c, cudaMemcpyAsync(fr.out_invalid, s.out_invalid, packed, cudaMemcpyDeviceToHost, st));
+  {
+    uint32_t n_copied = 0;
+    VX_CUDA(c, copy_out_kind(0, nb, OUT_LABEL, st, late_labels, &n_copied));
+    VX_CUDA(c, copy_out_kind(0, nb, OUT_BIN, st, late_labels, &n_copied));
+    VX_CUDA(c, copy_out_kind(0, nb, OUT_OCCLUDED, st, every, &n_copied));
+    VX_CUDA(c, copy_out_kind(0, nb, OUT_INVALID, st, every, &n_copied));
   }
   if (any_early) {
     VX_CUDA(c, cudaEventRecord(c->ev_copy_out, c->copy_out));
@@ -978,12 +1033,12 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   }
   c->lanes[0].stream = c->stream;
   {
-    // developer switches (A/B on the device): VX_B200_LANES = batches in flight (1 .. 4, default 3), VX_B200_FILL_PRIO=0 keeps
-    // the fill / vote / emit kernels on the lane's own stream
+    // developer switches (A/B on the device, profiles/r02_lanes_shapes_ab.txt): VX_B200_LANES = batches in flight (1 .. 4,
+    // default 2), VX_B200_FILL_PRIO=1 puts the fill / vote / emit kernels on a high-priority stream of the lane
     int lo_prio = 0, hi_prio = 0;
     VX_CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
     const char* e = std::getenv("VX_B200_FILL_PRIO");
-    const bool fill_prio = (!e || std::atoi(e) != 0) && hi_prio < lo_prio;
+    const bool fill_prio = e && std::atoi(e) != 0 && hi_prio < lo_prio;
     for (uint32_t k = 0; k < kMaxLanes; ++k) {
       Lane& ln = c->lanes[k];
       if (k > 0) VX_CREATE_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
@@ -1052,7 +1107,7 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   if (options) {
     if (options->table_log2_capacity) c->log2_target = options->table_log2_capacity;
     c->keep_tables = (options->debug & 1u) != 0;
-    c->vis_mode = options->vis_mode <= 2u ? (int)options->vis_mode : 0;
+    c->vis_mode = options->vis_mode <= 3u ? (int)options->vis_mode : 0;
     c->occlusion_labels = options->occlusion_labels != 0;
   }
   if (c->log2_target < 10) c->log2_target = 10;
@@ -1072,10 +1127,12 @@ int vx_create(int device, const vx_grid_desc* grid, const vx_filter_desc* filter
   uint32_t want = options && options->frames_in_flight ? options->frames_in_flight : 4u * resident;
   if (c->keep_tables && want > 8u && !(options && options->frames_in_flight)) want = 8u;  // debug: small batches,
   if (c->keep_tables || want < c->table_sets) c->table_sets = want;                       // every frame its own tables
-  // Three batches in flight (three lanes, each with frame records for a whole batch) unless the tables are kept for debugging or
-  // a scratch buffer per resident CTA (needed once CTAs of several launches share the SMs) does not fit next to everything else.
+  // Two batches in flight (two lanes, each with frame records for a whole batch) unless the tables are kept for debugging or a
+  // scratch buffer per resident CTA (needed once CTAs of several launches share the SMs) does not fit next to everything else.
+  // (Measured: with two lanes the 1036 traversal slots are already full all the time; three or four lanes give the same
+  // 495 frames/s, with or without the high-priority fill stream.)
   if (const char* e = std::getenv("VX_B200_LEAVE_ROOM")) c->leave_room = std::atoi(e) != 0;
-  c->depth = 3;
+  c->depth = 2;
   if (const char* e = std::getenv("VX_B200_LANES")) {
     const int n = std::atoi(e);
     if (n >= 1 && n <= (int)kMaxLanes) c->depth = (uint32_t)n;

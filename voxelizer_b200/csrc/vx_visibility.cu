@@ -39,6 +39,7 @@
 // one fire-and-forget RED per ray step, one hit-bit gather per live visit.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "vx_launch.h"
@@ -1113,12 +1114,23 @@ using CfgThroughput = VisCfg<VX_THR_THREADS, VX_THR_MAXLIVE, 256, VX_THR_CTAS, V
 #define VX_LAT_THREADS 512
 #endif
 using CfgLatency = VisCfg<VX_LAT_THREADS, 8192, 1024, 1>;
+// MIDDLE shape: 256 threads, waves of <= 2560 live cells, 4 CTAs per SM (64 registers) -- for batches that give every SM two to
+// four frames (a rank's share of a sequence split over eight GPUs: 568 frames): twice the threads per frame of the throughput
+// shape on the same register file.
+#ifndef VX_MID_THREADS
+#define VX_MID_THREADS 256
+#define VX_MID_MAXLIVE 2560
+#define VX_MID_CTAS 4
+#endif
+using CfgMid = VisCfg<VX_MID_THREADS, VX_MID_MAXLIVE, 512, VX_MID_CTAS>;
 
 constexpr size_t kRoomySmem = 36 * 1024;  // 6 x (36 + 1) KB fit an SM, 7 do not
 
 cudaError_t vx_visibility_prepare() {
   cudaError_t e = cudaFuncSetAttribute(vx_visibility_kernel<CfgThroughput>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)std::max(sizeof(VisShared<CfgThroughput>), kRoomySmem));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(vx_visibility_kernel<CfgMid>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisShared<CfgMid>));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(vx_visibility_kernel<CfgLatency>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VisShared<CfgLatency>));
 }
@@ -1130,11 +1142,14 @@ int vx_visibility_resident_ctas(int device) {
                                                     sizeof(VisShared<CfgThroughput>)) != cudaSuccess) return 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, vx_visibility_kernel<CfgLatency>, CfgLatency::kThreads,
                                                     sizeof(VisShared<CfgLatency>)) != cudaSuccess) return 0;
+  int m = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, vx_visibility_kernel<CfgMid>, CfgMid::kThreads, sizeof(VisShared<CfgMid>)) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
-  return (a > b ? a : b) * sms;
+  return std::max(a, std::max(b, m)) * sms;
 }
 
-// mode: 0 = by batch size (latency shape when the frames cannot even give every SM two CTAs), 1 = throughput, 2 = latency.
+// mode: 0 = by batch size (latency shape when the frames cannot even give every SM two CTAs, middle shape up to four per SM),
+// 1 = throughput, 2 = latency, 3 = middle.
 // leave_room: another batch is in flight or queued -- the throughput shape then asks for a little more shared memory than it uses,
 // so that an SM holds 6 instead of 7 of its CTAs and keeps registers for one CTA of the other batch's fill / vote / emit kernels
 // (which otherwise crawl behind ~900 resident traversal CTAs: 294 / 175 / 478 ms instead of 40 / 3 / 6 per step).
@@ -1146,9 +1161,13 @@ cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, 
   if (mode == 0) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    mode = n_slots <= 2u * (uint32_t)sms ? 2 : 1;
+    static const bool mid_auto = [] { const char* e = std::getenv("VX_B200_MID_SHAPE"); return !e || std::atoi(e) != 0; }();  // (=0: A/B)
+    mode = n_slots <= 2u * (uint32_t)sms ? 2 : ((mid_auto && n_slots <= (uint32_t)CfgMid::kCtasPerSm * (uint32_t)sms) ? 3 : 1);
   }
-  if (mode == 2)
+  if (mode == 3)
+    vx_visibility_kernel<CfgMid><<<n_slots, CfgMid::kThreads, sizeof(VisShared<CfgMid>), stream>>>(
+        slots, frames, endpoints, geom, hit_words, scratch, n_scratch, locks);
+  else if (mode == 2)
     vx_visibility_kernel<CfgLatency><<<n_slots, CfgLatency::kThreads, sizeof(VisShared<CfgLatency>), stream>>>(
         slots, frames, endpoints, geom, hit_words, scratch, n_scratch, locks);
   else {
