@@ -51,7 +51,7 @@ for setting in args.settings:
     os.environ["VX_B200_LANES"] = parts[0]
     os.environ["VX_B200_FILL_PRIO"] = parts[1] if len(parts) > 1 else "1"
     os.environ["VX_B200_LEAVE_ROOM"] = parts[2] if len(parts) > 2 else "0"
-    be = vx.Backend.from_config(cfg)
+    be = vx.Backend.from_config(cfg, vis_mode=int(os.environ.get("VX_DEV_VIS_MODE", "0")))
     lanes = be.batches_in_flight
     for t in range(args.scans):
         be.upload_scan_ptr(t, pin_x.ptr + t * CAP * 16, pin_l.ptr + t * CAP * 4, int(counts[t]))
