@@ -513,9 +513,12 @@ def test_thousand_frame_job_is_deterministic():
     counts = vx.synth_generate_many(params, 0, n_scans, xyzr.ctypes.data, lab.ctypes.data, cap)
     poses = vx.synth_velo_poses(params, n_scans).astype(np.float32)
     cfg = vx.Config(cfg_path("semantic_kitti_dense"))
-    be = vx.Backend(cfg.pod.voxelSize, list(cfg.pod.minExtent)[:3], list(cfg.pod.maxExtent)[:3], cfg.pod.minRange, cfg.pod.maxRange)
+    be = vx.Backend(cfg.pod.voxelSize, list(cfg.pod.minExtent)[:3], list(cfg.pod.maxExtent)[:3], cfg.pod.minRange, cfg.pod.maxRange,
+                    vis_mode=1)  # (left to itself the library would give a batch just above 1036 frames the middle shape)
+    auto = vx.Backend(cfg.pod.voxelSize, list(cfg.pod.minExtent)[:3], list(cfg.pod.maxExtent)[:3], cfg.pod.minRange, cfg.pod.maxRange)
     for t in range(n_scans):
         be.upload_scan(t, xyzr[t, : counts[t]], lab[t, : counts[t]])
+        auto.upload_scan(t, xyzr[t, : counts[t]], lab[t, : counts[t]])
     specs = []
     for target in range(1040):
         past = np.arange(target + 1, target + 15, dtype=np.uint32)    # 14 past scans: 14 invalid passes per frame
@@ -536,11 +539,12 @@ def test_thousand_frame_job_is_deterministic():
     assert digests[0] == digests[1]
     # the first 560 frames alone: a batch of 2 - 4 frames per SM runs in the MIDDLE shape (4 x 256-thread CTAs per SM, all of them
     # resident at once) -- same bytes as the throughput shape gave above
-    part = be.process(specs[:560])
+    part = auto.process(specs[:560])
     for a, b in zip(part, outs[:560]):
         for k in ("bin", "label", "occluded", "invalid"):
             assert np.array_equal(a[k], b[k]), k
     del part
+    auto.close()
     for o in outs[::97]:
         occl = np.unpackbits(o["occluded"], bitorder="big").astype(bool)
         inv = np.unpackbits(o["invalid"], bitorder="big").astype(bool)

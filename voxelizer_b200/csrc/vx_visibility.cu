@@ -1148,8 +1148,8 @@ int vx_visibility_resident_ctas(int device) {
   return std::max(a, std::max(b, m)) * sms;
 }
 
-// mode: 0 = by batch size (latency shape when the frames cannot even give every SM two CTAs, middle shape up to four per SM),
-// 1 = throughput, 2 = latency, 3 = middle.
+// mode: 0 = by batch size (latency shape when the frames cannot even give every SM two CTAs, middle shape up to four per SM and
+// for batches a little larger than the throughput shape's 7 per SM), 1 = throughput, 2 = latency, 3 = middle.
 // leave_room: another batch is in flight or queued -- the throughput shape then asks for a little more shared memory than it uses,
 // so that an SM holds 6 instead of 7 of its CTAs and keeps registers for one CTA of the other batch's fill / vote / emit kernels
 // (which otherwise crawl behind ~900 resident traversal CTAs: 294 / 175 / 478 ms instead of 40 / 3 / 6 per step).
@@ -1162,7 +1162,13 @@ cudaError_t vx_launch_visibility(const VxSlot* slots, const VxVisFrame* frames, 
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static const bool mid_auto = [] { const char* e = std::getenv("VX_B200_MID_SHAPE"); return !e || std::atoi(e) != 0; }();  // (=0: A/B)
-    mode = n_slots <= 2u * (uint32_t)sms ? 2 : ((mid_auto && n_slots <= (uint32_t)CfgMid::kCtasPerSm * (uint32_t)sms) ? 3 : 1);
+    // Measured (profiles/r02_middle_shape_ab.txt): the middle shape wins where the throughput shape would run with few frames
+    // per SM (568 frames: 1.23 s against 1.73 s) and where it would need a second, nearly empty round (1136 frames on 1036
+    // slots: 2.40 s against 3.00 s); the throughput shape wins when everything is resident at once (909 frames: 2.02 s against
+    // 2.30 s); for many rounds the two are equal (489 / 495 frames/s under streaming load).
+    const uint32_t thr_slots = (uint32_t)CfgThroughput::kCtasPerSm * (uint32_t)sms, mid_slots = (uint32_t)CfgMid::kCtasPerSm * (uint32_t)sms;
+    const bool mid = mid_auto && (n_slots <= mid_slots || (n_slots > thr_slots && n_slots <= mid_slots * 5u / 2u));
+    mode = n_slots <= 2u * (uint32_t)sms ? 2 : (mid ? 3 : 1);
   }
   if (mode == 3)
     vx_visibility_kernel<CfgMid><<<n_slots, CfgMid::kThreads, sizeof(VisShared<CfgMid>), stream>>>(
