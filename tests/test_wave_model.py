@@ -89,3 +89,34 @@ def test_rays_in_flight_formulation_matches_oracle(shape, dens):
     assert parked > 0
     if dens < 0.1:
         assert redone > 0, "no pass was run again: the endpoints on voxel faces no longer make rays miss their end voxel?"
+
+
+@pytest.mark.parametrize("shape", [((0, -4, -1), (8, 4, 1), 0.5), ((0, -20, -2), (40, 20, 1), 0.6), ((-3, -2, -1), (5, 7, 2.5), 0.5)])
+@pytest.mark.parametrize("dens", [0.002, 0.03, 0.25])
+def test_mark_filter_formulation_matches_oracle(shape, dens):
+    """Model mode 2 (studied in round 2, profiles/r02_memo_layout_study.txt): a ray skips the memo mark of every cell whose
+    2^s x 2^s x 1 block held no live cell when the pass began -- only snapshots of LIVE cells ever read the memo, and a cell that is
+    dead at the start of a pass stays dead.  Same bits as the reference, the same rays and steps, and some marks really are skipped."""
+    orc = Oracle("port")
+    mn, mx, res = shape
+    rng = np.random.default_rng(int(dens * 1000) + 11 * len(str(shape)))
+    g = orc.grid(res, mn, mx)
+    n = int(g.nvox * dens) + 1
+    pts = np.column_stack([rng.uniform(mn[a] - 0.5, mx[a] + 0.5, n) for a in range(3)] + [np.ones(n)]).astype(np.float32)
+    eps = np.column_stack([rng.uniform(mn[a] - 2, mx[a] + 2, 6) for a in range(3)]).astype(np.float32)
+    g.insert(pts, np.ones(n, np.uint32))
+    g.update_occlusions()
+    for e in eps:
+        g.update_invalid(e)
+    occ_f, inv_f = g.flags()
+    occb = (g.to_output_order(g.counts()) > 0).astype(np.uint8)
+    skipped = 0
+    for block_shift in (1, 2, 3):
+        for wave_cells in (4096, 64):
+            o, iv, st, extra = run_model(g, occb, eps, wave_cells | (block_shift << 24), seed=wave_cells + block_shift, mode=2)
+            assert st[7] == 0
+            assert np.array_equal(o, occ_f) and np.array_equal(iv, inv_f), (block_shift, wave_cells)
+            o0, iv0, st0 = run_model(g, occb, eps, wave_cells, seed=wave_cells + block_shift)
+            assert st[0] == st0[0] and st[1] == st0[1] and int(extra[1]) == int(st[1])   # the same rays and steps; one mark per step
+            skipped += int(extra[0])
+    assert skipped > 0
