@@ -1,10 +1,11 @@
-"""Developer check run on a GPU box: product gen_data vs the oracle port on fresh synthetic sequences."""
+"""Developer check run on a GPU box: product gen_data vs the oracle port on fresh synthetic sequences.
+(Lives under tests/: only test code may import the oracle.)"""
 import filecmp, os, shutil, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import voxelizer_b200 as vx
 from oracle.oracle import Oracle
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def compare(a, b):
     fa, fb = sorted(os.listdir(a)), sorted(os.listdir(b))

@@ -1,6 +1,6 @@
 """Small cases for `compute-sanitizer --tool memcheck|racecheck` (run on a GPU box, one tool per gpurun call):
 
-    compute-sanitizer --tool racecheck python tools/sanitize_case.py > gpurun_out/racecheck.log 2>&1
+    compute-sanitizer --tool racecheck python tests/dev/sanitize_case.py > gpurun_out/racecheck.log 2>&1
 
 Both shapes of the traversal kernel, the fill / vote / emit / pack kernels, the public ray, asynchronous submission; every
 output is compared with the oracle so that a run the sanitizer slows down 100x still proves it computed the right bytes."""
@@ -9,7 +9,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # (under tests/: only test code may import the oracle)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
